@@ -1,0 +1,218 @@
+/*
+ * iivision_b200.h -- C ABI of libiivision_b200.so (sm_100a).
+ *
+ * The reference (KrisKennaway/ii-vision) is pure Python with no FFI; the
+ * drop-in boundary is therefore the set of Python functions/methods on its two
+ * hot paths.  Each entry point below is what a ctypes binding for that
+ * function would call; the reference symbol it replaces is cited as
+ * file:line relative to the reference tree (transcoder/...).  INTEGRATION.md
+ * shows the reference-side ctypes stubs.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t, or a
+ *     negative IIV_E_* code; iiv_last_error() gives a thread-local message.
+ *   - "d_" pointers are device pointers, "h_" pointers are host pointers.  The
+ *     caller owns every buffer; the library keeps no pointer after a call.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Work
+ *     is stream-ordered; functions taking only d_ pointers do not synchronise.
+ *   - mode: IIV_MODE_HGR (screen.py:550 HGRBitmap) or IIV_MODE_DHGR
+ *     (screen.py:819 DHGRBitmap).
+ *   - tables are uint16[n_offsets][4^masked_bits], entry index
+ *     (i << masked_bits) + j  (make_data_tables.py:133-135, 163).
+ */
+#ifndef IIVISION_B200_H_
+#define IIVISION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IIV_MODE_HGR 0
+#define IIV_MODE_DHGR 1
+
+#define IIV_E_BADARG (-1)
+#define IIV_E_UNSUPPORTED (-2)
+#define IIV_E_OVERFLOW (-3)
+
+/* Table layouts for iiv_table_generate. */
+#define IIV_LAYOUT_TRIANGULAR 0 /* j < i only, zeros elsewhere: the reference's
+                                   .npz layout (make_data_tables.py:156-172) */
+#define IIV_LAYOUT_SYMMETRIC 1  /* full square: what Bitmap.edit_distances
+                                   returns after its transpose-add
+                                   (screen.py:358-365) */
+
+/* Generator kernels. */
+#define IIV_ALGO_AUTO 0
+#define IIV_ALGO_CHAIN 1 /* one independent 1-D recurrence per entry */
+#define IIV_ALGO_TREE 2  /* shared-suffix tree over a block of j per thread */
+
+const char* iiv_last_error(void);
+int iiv_version(void);
+
+/* Class constants: MASKED_BITS, MASKED_DOTS, len(BYTE_MASKS), PHASES
+ * (screen.py:617-645 HGR, :887-919 DHGR). phases4 receives n_offsets values. */
+int iiv_mode_info(int mode, int* masked_bits, int* masked_dots, int* n_offsets,
+                  int* phases4);
+
+/* ---- path 1: edit-distance tables (make_data_tables.py) ----------------- */
+
+/* compute_diff_matrix (make_data_tables.py:55-70): 16x16 int()-truncated
+ * CIE2000 dE between sRGB triples (colormath 3.0.0 pipeline, FP64, on the
+ * device).  h_rgb: 16 x 3 uint8 indexed by nominal colour value
+ * (colours.py:27-42); h_lut: 16 x 16 int32.  Synchronises. */
+int iiv_lut_cie2000(const uint8_t* h_rgb, int32_t* h_lut);
+/* Same, untruncated (diagnostics: distance of each entry to an integer). */
+int iiv_lut_cie2000_f64(const uint8_t* h_rgb, double* h_de);
+
+/* Bitmap.to_dots (screen.py:741-789 HGR, :982-990 DHGR) for every masked value:
+ * d_dots uint32[n_offsets][2^bits]. */
+int iiv_all_dots(int mode, uint32_t* d_dots, void* stream);
+/* colours.dots_to_nominal_colour_pixel_values (colours.py:137-148) for every
+ * masked value and offset: d_pix uint8[n_offsets][2^bits][masked_dots]. */
+int iiv_all_pixel_strings(int mode, uint8_t* d_pix, void* stream);
+
+/* compute_edit_distance (make_data_tables.py:111-174) with edit_distance
+ * (:92-108) inlined: fills rows [row_begin,row_end) of the source index i, for
+ * every offset, of d_table (the FULL table base pointer).  h_lut: the 16x16
+ * substitution costs (compute_substitute_costs, :73-89), each 0..255.
+ * Insert/delete are never taken (cost 1e5, :35-36), transposition costs 1. */
+int iiv_table_generate(int mode, const int32_t* h_lut, uint16_t* d_table,
+                       uint32_t row_begin, uint32_t row_end, int layout,
+                       int algo, void* stream);
+
+/* edit_distance (make_data_tables.py:92-108) for n_pairs explicit pixel strings
+ * of `len` nibble-valued pixels each (d_a, d_b: uint8[n_pairs][len]); d_out
+ * int32[n_pairs]. */
+int iiv_string_distance(const int32_t* h_lut, const uint8_t* d_a,
+                        const uint8_t* d_b, int n_pairs, int len,
+                        int32_t* d_out, void* stream);
+
+/* Fused generate + all-gather over NVLink peer memory: rank `rank` of `n_ranks`
+ * computes its row block and stores it into every rank's table
+ * (h_peer_tables[r] = device pointer of rank r's table, peer-mapped).  If
+ * d_multicast_table is non-NULL the block is stored once through the NVSwitch
+ * multicast mapping instead.  Callers barrier afterwards. */
+int iiv_table_generate_scatter(int mode, const int32_t* h_lut,
+                               uint16_t* const* h_peer_tables, int n_ranks,
+                               int rank, uint16_t* d_multicast_table,
+                               uint32_t row_begin, uint32_t row_end, int layout,
+                               void* stream);
+
+/* Bitmap.edit_distances' in-memory transform (screen.py:358-365):
+ * new[y] = old[y] + old[transpose(y)], in place, all offsets. */
+int iiv_table_symmetrise(int mode, uint16_t* d_table, void* stream);
+
+/* ---- path 2: per-frame scorer (screen.py) ------------------------------- */
+
+/* Bitmap._pack (screen.py:207-226; _body/_make_header/_make_footer :650-690 HGR,
+ * :921-952 DHGR).  d_main/d_aux: uint8[batch][32][256] (d_aux NULL for HGR);
+ * d_packed: uint64[batch][32][128].  Strides in bytes between batch items. */
+int iiv_pack(int mode, const uint8_t* d_main, const uint8_t* d_aux,
+             size_t mem_stride, uint64_t* d_packed, int batch, void* stream);
+
+/* Bitmap.mask_and_shift_data (screen.py:369-378), elementwise over n words. */
+int iiv_mask_and_shift(int mode, int byte_offset, const uint64_t* d_in,
+                       uint64_t* d_out, size_t n, void* stream);
+
+/* HGRBitmap/DHGRBitmap.masked_update (screen.py:791-816, :992-1007),
+ * elementwise over n words (no neighbour fix-up). */
+int iiv_masked_update(int mode, int byte_offset, const uint64_t* d_old,
+                      uint8_t value, uint64_t* d_new, size_t n, void* stream);
+
+/* Bitmap._fix_array_neighbours (screen.py:322-341) on rows of 128 words. */
+int iiv_fix_array_neighbours(int mode, int byte_offset, uint64_t* d_rows,
+                             int n_rows, void* stream);
+
+/* Bitmap.diff_weights / _diff_weights (screen.py:400-449): d_out
+ * int32[batch][32][256]; source/target uint64[batch][32][128]; d_table is the
+ * SYMMETRIC table.  content < 0 means "no content" (the diff_weights call);
+ * content >= 0 evaluates every cell as if `content` were stored there. */
+int iiv_diff_weights(int mode, int is_aux, const uint64_t* d_source_packed,
+                     const uint64_t* d_target_packed, int content,
+                     const uint16_t* d_table, int32_t* d_out, int batch,
+                     void* stream);
+
+/* Bitmap._diff_weights_page (screen.py:453-494) on n_rows rows of 128 words:
+ * d_out int32[n_rows][256]. */
+int iiv_diff_weights_page(int mode, int is_aux, const uint64_t* d_source_rows,
+                          const uint64_t* d_target_rows, int content,
+                          const uint16_t* d_table, int32_t* d_out, int n_rows,
+                          void* stream);
+
+/* Bitmap.compute_delta_page (screen.py:525-547): d_out[256] =
+ * _diff_weights_page(row, row, is_aux, content) - d_diff_row[256]. */
+int iiv_compute_delta_page(int mode, int is_aux,
+                           const uint64_t* d_target_packed, int page,
+                           int content, const int32_t* d_diff_row,
+                           const uint16_t* d_table, int32_t* d_out,
+                           void* stream);
+
+/* Every compute_delta_page "new_diff" row of one target frame-bank at once:
+ * d_out uint16[batch][32][n_content][256], n_content = 256 (HGR) / 128 (DHGR). */
+int iiv_delta_rows(int mode, int is_aux, const uint64_t* d_target_packed,
+                   const uint16_t* d_table, uint16_t* d_out, int batch,
+                   void* stream);
+
+/* Bitmap.byte_pair_difference (screen.py:383-398) for n (packed word, content)
+ * pairs: d_out uint16[n]. */
+int iiv_byte_pair_difference(int mode, int byte_offset,
+                             const uint64_t* d_old_packed,
+                             const uint8_t* d_content, const uint16_t* d_table,
+                             uint16_t* d_out, size_t n, void* stream);
+
+/* Bitmap.apply + _fix_scalar_neighbours + MemoryMap.write (screen.py:256-293,
+ * :122-125) for a sequence of n stores applied in order to ONE bitmap:
+ * h_stores = n x (page, offset, is_aux, value) int32 quadruples. */
+int iiv_apply(int mode, uint64_t* d_packed, uint8_t* d_main, uint8_t* d_aux,
+              const int32_t* h_stores, int n, void* stream);
+
+/* ---- path 2: encoder (video.py) ------------------------------------------ */
+
+/* Per-clip encoder state blob (Video.__init__, video.py:21-62), one per clip,
+ * `iiv_clip_state_bytes()` bytes each, layout given by iiv_clip_state_layout:
+ *   [0] packed        uint64[32][128]  Video.pixelmap.packed
+ *   [1] main memory   uint8[32][256]   Video.memory_map.page_offset
+ *   [2] aux memory    uint8[32][256]   Video.aux_memory_map.page_offset
+ *   [3] priority main int32[32][256]   Video.update_priority
+ *   [4] priority aux  int32[32][256]   Video.aux_update_priority
+ *   [5] mt_numpy      uint32[625]      np.random global MT19937 key + pos
+ *   [6] mt_python     uint32[625]      random module MT19937 state + index
+ *   [7] flags         int32[8]         [0]=out_of_work main, [1]=out_of_work aux
+ */
+#define IIV_CLIP_STATE_FIELDS 8
+size_t iiv_clip_state_bytes(void);
+int iiv_clip_state_layout(size_t* offsets8);
+
+/* Video.encode_frame / _index_changes / _heapify_priorities / _compute_error
+ * (video.py:72-301) for n_clips independent clips, one thread block per clip,
+ * running the same schedule of n_segments (frame, is_aux, budget) segments
+ * (one segment = one encode_frame generator pulled `budget` times).
+ *   d_state          n_clips state blobs, state_stride bytes apart
+ *   d_target_mem     uint8[n_clips][n_frames][banks][32][256]
+ *   d_target_packed  uint64[n_clips][n_frames][32][128] (iiv_pack of the above)
+ *   h_segments       int32[n_segments][3]
+ *   d_table          symmetric table of the mode
+ *   d_opcodes        uint8[n_clips][sum(budget)][8]: page+32, content, o0..o3,
+ *                    flag (1 = real opcode, 0 = out-of-work padding), 0
+ *   d_seg_info       int64[n_clips][n_segments][4]: real opcodes emitted,
+ *                    sum of update_priority before the segment (video.py:90),
+ *                    numpy-stream words drawn, python-stream words drawn
+ */
+int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
+                     size_t state_stride, const uint8_t* d_target_mem,
+                     const uint64_t* d_target_packed, int n_frames,
+                     const int32_t* h_segments, int n_segments,
+                     const uint16_t* d_table, uint8_t* d_opcodes,
+                     int64_t* d_seg_info, void* stream);
+
+/* MT19937 helpers used by the Python facade to keep the process-global
+ * generators in step (device-side draws, host-visible state). */
+int iiv_mt_draw(uint32_t* d_mt625, uint32_t* d_words, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IIVISION_B200_H_ */
