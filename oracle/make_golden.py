@@ -1,0 +1,230 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference modules.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+The reference cannot travel to the GPU box, so its outputs do, as fixtures:
+
+  pixel_strings.json   SHA-256 of to_dots / nominal-colour pixel strings for every
+                       masked value (reference screen.py:741-789, :982-990;
+                       colours.py:137-148)
+  scorer_<mode>.npz    _pack, mask_and_shift_data, masked_update, apply,
+                       diff_weights, compute_delta_page, byte_pair_difference
+                       outputs of the reference Bitmap classes on seeded screens
+                       (screen.py:207-547)
+  stream_<case>.npz    opcode tuples pulled from the reference
+                       Video.encode_frame (video.py:72-301) under the Movie.encode
+                       schedule, with random.seed(s); np.random.seed(s), plus the
+                       encoder state and the next words of both RNG streams
+  luts.json            int(dE2000) substitution matrices from oracle/cie2000.py
+                       (restated colormath; NOT reference output -- the reference
+                       generator cannot run offline) together with the rows
+                       recorded in SURVEY.md Appendix C
+
+The edit-distance tables fed to the reference scorer are the oracle's
+(oracle/tables.py); the scorer's arithmetic is independent of their contents.
+"""
+
+import hashlib
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from iivision_b200 import synth  # noqa: E402  (frame generator only; no CUDA)
+from oracle import ref_harness, tables  # noqa: E402
+
+STREAM_CASES = [
+    # name, mode, frames, fraction, frame seed, rng seed, opcodes/frame, flip
+    ("dhgr_full", "DHGR", 3, 1.0, 1, 0, 980, 292),
+    ("dhgr_sparse", "DHGR", 4, 0.05, 2, 7, 980, 292),
+    ("hgr_full", "HGR", 3, 1.0, 3, 0, 980, 292),
+    ("hgr_sparse", "HGR", 4, 0.02, 4, 11, 600, 292),
+]
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def symmetric_table(mode, pid=5):
+    tab, _ = tables.build_table(mode, tables.substitution_lut(pid))
+    return tables.symmetrise(mode, tab)
+
+
+def ref_bitmap(ns, mode, main, aux=None):
+    mm = ns.screen.MemoryMap(screen_page=1, page_offset=main)
+    if mode == "DHGR":
+        am = ns.screen.MemoryMap(screen_page=1, page_offset=aux)
+        return ns.screen.DHGRBitmap(palette=ns.palette.Palette.NTSC,
+                                    main_memory=mm, aux_memory=am)
+    return ns.screen.HGRBitmap(palette=ns.palette.Palette.NTSC, main_memory=mm)
+
+
+def gen_pixel_strings(ns):
+    out = {}
+    for mode, cls, cols in (("HGR", ns.screen.HGRBitmap, ns.colours.HGRColours),
+                            ("DHGR", ns.screen.DHGRBitmap, ns.colours.DHGRColours)):
+        bits, n = int(cls.MASKED_BITS), int(cls.MASKED_DOTS)
+        dots = np.zeros((len(cls.PHASES), 1 << bits), dtype=np.uint32)
+        pix = np.zeros((len(cls.PHASES), 1 << bits, n), dtype=np.uint8)
+        for o, ph in enumerate(cls.PHASES):
+            for v in range(1 << bits):
+                d = cls.to_dots(v, o)
+                dots[o, v] = d
+                pix[o, v] = ns.colours.dots_to_nominal_colour_pixel_values(
+                    n, d, cols, init_phase=ph)
+        out[mode] = {"dots_sha256": sha(dots), "pixels_sha256": sha(pix),
+                     "dots_max": int(dots.max()), "pixels_sum": int(pix.sum()),
+                     "shape": list(pix.shape)}
+    with open(os.path.join(GOLDEN, "pixel_strings.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+def gen_scorer(ns, mode, table):
+    ref_harness.install_tables(ns, mode, {5: table})
+    fr = synth.synthetic_frames(mode, 2, 1.0, seed=21)
+    if mode == "HGR":
+        fr[1, 0, 3, :40] = 0xFF       # palette bits set across a run
+        fr[1, 0, 4, :40] = 0x80
+    src = ref_bitmap(ns, mode, fr[0, 0].copy(), fr[0, 1].copy() if mode == "DHGR" else None)
+    tgt = ref_bitmap(ns, mode, fr[1, 0].copy(), fr[1, 1].copy() if mode == "DHGR" else None)
+    cls = type(src)
+    noff = len(cls.BYTE_MASKS)
+    out = {"frames": fr, "src_packed": src.packed.copy(), "tgt_packed": tgt.packed.copy()}
+    rng = np.random.default_rng(5)
+    width = int(cls.HEADER_BITS + cls.BODY_BITS + cls.FOOTER_BITS)
+    words = rng.integers(0, 1 << width, size=(4, 128), dtype=np.uint64)
+    out["words"] = words
+    values = np.array([0, 1, 0x55, 0x7F, 0x80, 0xFF], dtype=np.uint8)
+    out["values"] = values
+    ms = np.zeros((noff,) + words.shape, np.uint64)
+    mu = np.zeros((noff, len(values)) + words.shape, np.uint64)
+    for o in range(noff):
+        ms[o] = cls.mask_and_shift_data(words, o)
+        for k, v in enumerate(values):
+            mu[o, k] = cls.masked_update(o, words.copy(), np.uint8(v))
+    out["mask_shift"] = ms
+    out["masked_update"] = mu
+    banks = (False, True) if mode == "DHGR" else (False,)
+    for is_aux in banks:
+        tag = "aux" if is_aux else "main"
+        dw = tgt.diff_weights(src, is_aux)
+        out["diff_weights_" + tag] = dw.astype(np.int32)
+        cases = [(0, 0), (3, 0x55), (31, 0x7F), (17, 0x2A), (4, 0x7F if mode == "DHGR" else 0xFF),
+                 (3, 0x00 if mode == "DHGR" else 0x80)]
+        deltas = np.zeros((len(cases), 256), np.int32)
+        for k, (page, content) in enumerate(cases):
+            deltas[k] = tgt.compute_delta_page(page, np.uint8(content), dw[page, :], is_aux)
+        out["delta_cases_" + tag] = np.array(cases, np.int32)
+        out["delta_" + tag] = deltas
+        bpd = []
+        for page, off, content in ((0, 0, 5), (3, 7, 0x7F), (9, 100, 0x33), (31, 119, 1)):
+            bo = cls.byte_offset(off, is_aux)
+            bpd.append((bo, page, off, content, int(tgt.byte_pair_difference(
+                bo, tgt.packed[page, off // 2], np.uint8(content)))))
+        out["pair_difference_" + tag] = np.array(bpd, np.int64)
+    # apply: a sequence of stores on the source bitmap (screen.py:256-293)
+    stores = []
+    rng = np.random.default_rng(9)
+    for _ in range(300):
+        page, off = int(rng.integers(0, 32)), int(rng.integers(0, 256))
+        is_aux = bool(rng.integers(0, 2)) if mode == "DHGR" else False
+        val = int(rng.integers(0, 128 if mode == "DHGR" else 256))
+        stores.append((page, off, int(is_aux), val))
+    stores += [(0, 0, 0, 0x7F), (0, 255, 0, 0x7F), (31, 254, 0, 1), (5, 1, 0, 0x40)]
+    for page, off, is_aux, val in stores:
+        src.apply(page, off, bool(is_aux), np.uint8(val))
+    out["apply_stores"] = np.array(stores, np.int32)
+    out["apply_packed"] = src.packed.copy()
+    out["apply_main"] = src.main_memory.page_offset.copy()
+    if mode == "DHGR":
+        out["apply_aux"] = src.aux_memory.page_offset.copy()
+    np.savez_compressed(os.path.join(GOLDEN, "scorer_%s.npz" % mode.lower()), **out)
+
+
+def gen_stream(ns, case, table):
+    name, mode, n_frames, fraction, fseed, seed, per_frame, flip = case
+    ref_harness.install_tables(ns, mode, {5: table})
+    frames = synth.synthetic_frames(mode, n_frames, fraction, seed=fseed)
+    segs = synth.movie_schedule(mode, n_frames, per_frame, flip)
+    vm = ns.video_mode.VideoMode.DHGR if mode == "DHGR" else ns.video_mode.VideoMode.HGR
+    random.seed(seed)
+    np.random.seed(seed)
+    v = ns.video.Video(ns.frame_grabber.FrameGrabber(vm), ticks_per_second=14700.,
+                       mode=vm, palette=ns.palette.Palette.NTSC)
+    ops, real, sims = [], [], []
+    for frame, is_aux, budget in segs:
+        is_aux = bool(is_aux)
+        tgt = ref_bitmap(ns, mode, frames[frame, 0].copy(),
+                         frames[frame, 1].copy() if mode == "DHGR" else None)
+        prio = v.aux_update_priority if is_aux else v.update_priority
+        sims.append(float(prio.mean()))
+        v.out_of_work = {True: False, False: False}
+        seq = v.encode_frame(tgt, is_aux)
+        for _ in range(budget):
+            page, content, offs = next(seq)
+            real.append(0 if v.out_of_work[is_aux] else 1)
+            ops.append([int(page), int(content)] + [int(o) for o in offs])
+    out = {
+        "mode": mode, "n_frames": n_frames, "fraction": fraction,
+        "frame_seed": fseed, "rng_seed": seed, "frames": frames,
+        "segments": np.array(segs, np.int32),
+        "opcodes": np.array(ops, np.uint8), "real": np.array(real, np.uint8),
+        "similarity": np.array(sims, np.float64),
+        "packed": v.pixelmap.packed.copy(),
+        "main": v.memory_map.page_offset.copy(),
+        "priority_main": v.update_priority.copy(),
+        "next_python_words": np.array(
+            [random.getrandbits(32) for _ in range(4)], np.uint32),
+        "next_numpy_bytes": np.random.randint(0, 256, size=4).astype(np.uint32),
+    }
+    if mode == "DHGR":
+        out["aux"] = v.aux_memory_map.page_offset.copy()
+        out["priority_aux"] = v.aux_update_priority.copy()
+    np.savez_compressed(os.path.join(GOLDEN, "stream_%s.npz" % name), **out)
+    print("  %s: %d opcodes, %d real" % (name, len(ops), int(np.sum(real))))
+
+
+def gen_luts():
+    survey_row0 = {
+        "5": [0, 35, 37, 50, 38, 39, 55, 64, 31, 53, 39, 65, 66, 78, 86, 99],
+        "0": [0, 44, 31, 49, 40, 24, 40, 60, 35, 57, 57, 66, 73, 101, 88, 99],
+    }
+    out = {"source": "oracle/cie2000.py (restated colormath 3.0.0; parity unpinned)",
+           "survey_row0": survey_row0, "lut": {}, "table_sha256": {}}
+    for pid in (0, 5):
+        lut = tables.substitution_lut(pid)
+        assert lut[0].tolist() == survey_row0[str(pid)]
+        out["lut"][str(pid)] = lut.tolist()
+        for mode in ("HGR", "DHGR"):
+            tab, _ = tables.build_table(mode, lut)
+            out["table_sha256"]["%s_%d" % (mode, pid)] = sha(tab)
+    with open(os.path.join(GOLDEN, "luts.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    ns = ref_harness.load()
+    print("pixel strings"); gen_pixel_strings(ns)
+    print("luts"); gen_luts()
+    for mode in ("HGR", "DHGR"):
+        table = symmetric_table(mode)
+        print("scorer", mode); gen_scorer(ns, mode, table)
+        for case in STREAM_CASES:
+            if case[1] == mode:
+                gen_stream(ns, case, table)
+
+
+if __name__ == "__main__":
+    main()
