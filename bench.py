@@ -1,0 +1,455 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ii-vision hot paths on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): HGR NTSC edit-distance table generation,
+2 byte offsets x 2^28 entries of uint16 (1 GiB), in the symmetric in-memory
+layout Bitmap.edit_distances hands to the scorer (reference screen.py:343-367).
+A step = one full table.  "entries" = elements of the uint16[n_off][4**bits]
+array delivered (the same count for every arm and layout).
+
+  value      table entries/s, table left resident in HBM (device-timed)
+  e2e        same through the reference-facing call
+             make_data_tables.compute_edit_distance(edp, HGRBitmap, HGRColours):
+             host parameters in, host numpy array out (D2H inside the timed region)
+  roofline   the generator kernel against HBM write bandwidth: 2 B/entry
+  cpu_baseline / --impl reference
+             the reference's CPU algorithm (oracle/tables_oracle.c faithful port:
+             per pair the full (n+2)^2 float64 Damerau-Levenshtein DP of
+             weighted_levenshtein.dam_lev, j < i only, make_data_tables.py:143-172)
+             on all host cores over a bounded sample of row blocks
+  scorer     secondary figures for the second hot path (DHGR frames/s), N=1 only
+
+N > 1: rows shard across ranks (strong scaling: one table, N GPUs) and an in-place
+NCCL all-gather leaves the whole table on every GPU.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODE = "HGR"
+PALETTE_ID = 5  # NTSC
+BITS, N_OFF, N_DOTS = 14, 2, 18
+ENTRIES = N_OFF * (1 << (2 * BITS))
+METRIC = "edit-distance table entries/s (HGR NTSC)"
+UNIT = "entries/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-scorer", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scorer-only", action="store_true",
+                    help="profiling aid: run just the second hot path's figures")
+    return ap.parse_args()
+
+
+# ---- CPU arm: the reference's algorithm on the host cores --------------------------
+
+def cpu_run_sample(tables, lut, out, n_rows):
+    """n_rows rows strided evenly over the whole index range, so the sample's
+    fill (j < i) is that of the whole triangle.  Returns (array entries
+    delivered, dam_lev evaluations, seconds)."""
+    n = 1 << BITS
+    step = max(1, n // n_rows)
+    t0 = time.perf_counter()
+    _, evals = tables.build_table(MODE, lut, step // 2, n, faithful=True,
+                                  triangular=True, out=out, row_step=step)
+    dt = time.perf_counter() - t0
+    rows = len(range(step // 2, n, step))
+    return rows * n * N_OFF, evals, dt
+
+
+def _cpu_rows_for(tables, lut, out, target_seconds, cores):
+    probe = max(8, cores)
+    _, _, dt = cpu_run_sample(tables, lut, out, probe)
+    rows = int(probe * target_seconds / max(dt, 1e-3))
+    return max(probe, min(1 << BITS, rows // cores * cores))
+
+
+def cpu_baseline(target_seconds=12.0):
+    import numpy as np
+    from oracle import tables
+    lut = tables.substitution_lut(PALETTE_ID)
+    out = np.zeros((N_OFF, 1 << (2 * BITS)), dtype=np.uint16)
+    cores = tables.max_threads()
+    rows = _cpu_rows_for(tables, lut, out, target_seconds, cores)
+    entries, evals, dt = cpu_run_sample(tables, lut, out, rows)
+    return {
+        "value": entries / dt, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": "%d rows strided evenly over the table (%d dam_lev evaluations, "
+                  "full (n+2)^2 float64 DP each, j<i only) in %.1f s; the whole HGR "
+                  "table extrapolates to %.0f s on these cores" % (
+                      rows, evals, dt, ENTRIES / (entries / dt)),
+        "dam_lev_per_s": evals / dt,
+    }
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import tables
+    lut = tables.substitution_lut(PALETTE_ID)
+    out = np.zeros((N_OFF, 1 << (2 * BITS)), dtype=np.uint16)
+    cores = tables.max_threads()
+    rows = _cpu_rows_for(tables, lut, out, 2.0, cores)   # ~2 s of CPU work per step
+    for _ in range(args.warmup):
+        cpu_run_sample(tables, lut, out, rows)
+    t0 = time.perf_counter()
+    entries = evals = 0
+    for _ in range(args.steps):
+        e, v, _ = cpu_run_sample(tables, lut, out, rows)
+        entries += e
+        evals += v
+    dt = time.perf_counter() - t0
+    value = entries / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (palette constants; no external data)",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {
+            "value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "each step: %d rows strided evenly over the table, full "
+                      "(n+2)^2 float64 dam_lev per pair (j<i), all host threads"
+                      % rows},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "HGR NTSC edit-distance table (make_data_tables.compute_edit_distance): "
+                    "2 offsets x 2^28 uint16 entries = 1 GiB, 18-pixel strings",
+        "layout": "symmetric (Bitmap.edit_distances form) for value; reference "
+                  "lower-triangular array for e2e",
+        "entries_per_step": ENTRIES,
+        "l2": "each step writes 1 GiB (> 126 MB L2); no explicit flush",
+        "parallelism": "rows sharded over %d GPU(s)%s" % (
+            n_gpus, " + in-place NCCL all-gather" if n_gpus > 1 else ""),
+    }
+
+
+# ---- clocks ------------------------------------------------------------------------------
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.15:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, parts[4:8]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- our arm ----------------------------------------------------------------------------------
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, ValueError):
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def scorer_figures(torch, ops):
+    """Second hot path, DHGR NTSC: (a) scoring primitives batched over frames
+    (pack + diff_weights + every delta row), (b) bit-exact encoding of
+    independent clips, one block per clip."""
+    import numpy as np
+    from iivision_b200 import palette, synth
+    lut = ops.lut_cie2000(palette.NTSCPalette.rgb_by_value())
+    table = ops.table_generate("DHGR", lut, layout=ops.LAYOUT_SYMMETRIC)
+    out = {}
+    # (a) phase A over a batch of 256 frame pairs
+    nb = 256
+    fr = synth.synthetic_frames("DHGR", 2, 1.0, seed=1)
+    main = torch.from_numpy(fr[:, 0]).cuda().repeat(nb // 2, 1, 1).contiguous()
+    aux = torch.from_numpy(fr[:, 1]).cuda().repeat(nb // 2, 1, 1).contiguous()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def phase_a():
+        packed = ops.pack("DHGR", main, aux)
+        src = torch.roll(packed, 1, 0).contiguous()
+        for is_aux in (0, 1):
+            ops.diff_weights("DHGR", is_aux, src, packed, table)
+    for _ in range(3):
+        phase_a()
+    torch.cuda.synchronize()
+    ev[0].record()
+    reps = 10
+    for _ in range(reps):
+        phase_a()
+    ev[1].record()
+    torch.cuda.synchronize()
+    out["scored_frames_per_s"] = nb * reps / (ev[0].elapsed_time(ev[1]) * 1e-3)
+    out["scored_frames_note"] = ("pack + diff_weights (main+aux banks) of %d DHGR frames "
+                                 "per launch set, device resident" % nb)
+    # (b) encoder: n_clips independent clips x n_frames, Movie.encode schedule
+    n_clips, n_frames = 148, 4
+    clips = np.stack([synth.synthetic_frames("DHGR", n_frames, 1.0, seed=100 + c)
+                      for c in range(4)])
+    clips = np.concatenate([clips] * (n_clips // 4 + 1))[:n_clips]
+    segs = synth.movie_schedule("DHGR", n_frames)
+    tmem = torch.from_numpy(np.ascontiguousarray(clips)).cuda()
+    flat = tmem.view(-1, 2, 32, 256)
+    tpacked = ops.pack("DHGR", flat[:, 0].contiguous(), flat[:, 1].contiguous()).view(
+        n_clips, n_frames, 32, 128)
+    import random
+    mt_py = ops.mt_from_python(random.Random(0).getstate())
+    mt_np = ops.mt_from_numpy(np.random.RandomState(0).get_state())
+
+    def fresh_states():
+        st = ops.new_clip_states(n_clips)
+        pad = np.zeros(640, np.uint32)
+        pad[:625] = mt_py
+        ops.state_field(st, ops.F_MT_PY, torch.int32, (640,)).copy_(
+            torch.from_numpy(pad.view(np.int32)).cuda().expand(n_clips, 640))
+        pad[:625] = mt_np
+        ops.state_field(st, ops.F_MT_NP, torch.int32, (640,)).copy_(
+            torch.from_numpy(pad.view(np.int32)).cuda().expand(n_clips, 640))
+        return st
+    ops.encode_clips("DHGR", fresh_states(), tmem, tpacked, segs, table)
+    torch.cuda.synchronize()
+    st = fresh_states()
+    ev[0].record()
+    opc, info = ops.encode_clips("DHGR", st, tmem, tpacked, segs, table)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1])
+    out["encoded_frames_per_s"] = n_clips * n_frames / (ms * 1e-3)
+    out["encoded_note"] = ("%d independent DHGR clips x %d frames, 980 opcodes/frame, bank "
+                           "flip every 292, one thread block per clip, bit-exact streams; "
+                           "single-clip rate = %.1f frames/s, %.2f us/opcode"
+                           % (n_clips, n_frames, n_frames / (ms * 1e-3),
+                              ms * 1e3 / (n_frames * 980)))
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    from iivision_b200 import colours, make_data_tables, ops, palette, parallel, screen
+
+    if args.scorer_only:
+        print(json.dumps({"scorer": scorer_figures(torch, ops)}))
+        return
+    pal = palette.NTSCPalette
+    edp = make_data_tables.compute_substitute_costs(pal)       # LUT on the device (FP64)
+    lut = make_data_tables._lut16(edp.substitute_costs)
+    table = torch.empty(ops.table_shape(MODE), dtype=torch.uint16, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step():
+        if world == 1:
+            ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
+        else:
+            parallel.generate_sharded(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3 if rank == 0 else 0)
+    t_load0 = time.perf_counter()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    t_host0 = time.perf_counter()
+    evs[0].record(stream)
+    for k in range(args.steps):
+        step()
+        evs[k + 1].record(stream)
+    barrier()
+    t_host1 = time.perf_counter()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = ENTRIES * args.steps / (total_ms * 1e-3)
+
+    # kernel-only timing for the roofline: the generator kernel(s) of this rank's rows
+    rows = parallel.row_partition(1 << BITS, world)[rank]
+    kev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    kernel_ms = []
+    for _ in range(min(args.steps, 10)):
+        kev[0].record(stream)
+        ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, row_begin=rows[0],
+                           row_end=rows[1], out=table)
+        kev[1].record(stream)
+        torch.cuda.synchronize()
+        kernel_ms.append(kev[0].elapsed_time(kev[1]))
+    # clocks over warm-up + timed region + the kernel-only loop (all back-to-back
+    # generator launches); the timed region alone can be shorter than one sample
+    clocks = sampler.summary(t_load0, time.perf_counter()) if sampler else None
+    k_ms = sum(kernel_ms) / len(kernel_ms)
+    peaks, peak_src = measured_peaks()
+    alg_bytes = 2.0 * ENTRIES / world
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+
+    # e2e through the reference-facing call: host in, host numpy out
+    e2e_steps = max(2, min(args.steps, 5))
+    shard = (rows[1] - rows[0]) * (1 << BITS) * N_OFF * 2
+    if world == 1:
+        def e2e_step():
+            edp_ = make_data_tables.compute_substitute_costs(pal)
+            return make_data_tables.compute_edit_distance(
+                edp_, screen.HGRBitmap, colours.HGRColours)
+    else:
+        host = torch.empty((N_OFF, (rows[1] - rows[0]) << BITS), dtype=torch.uint16,
+                           pin_memory=True)
+
+        def e2e_step():
+            # every rank generates its row block and copies only that block home
+            ops.table_generate(MODE, lut, layout=ops.LAYOUT_TRIANGULAR, row_begin=rows[0],
+                               row_end=rows[1], out=table)
+            view = table.view(N_OFF, 1 << BITS, 1 << BITS)[:, rows[0]:rows[1]]
+            host.view(N_OFF, rows[1] - rows[0], 1 << BITS).copy_(view, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return host
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    del res
+    if sampler:
+        sampler.stop()
+
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic (palette constants; no external data)",
+        "config": workload_config(world),
+        "clocks": clocks,
+        "e2e": {"value": ENTRIES * e2e_steps / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": 16 * 3 + 256 * 4,
+                "d2h_bytes_per_step": (2 * ENTRIES if world == 1 else shard) + 256 * 4,
+                "steps": e2e_steps,
+                "call": "make_data_tables.compute_substitute_costs + compute_edit_distance "
+                        "-> host uint16 array" if world == 1 else
+                        "per-rank row block generate + D2H of that block"},
+        "gpu_launches": ops.launches_per_table_generate() * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                     "peak_source": peak_src, "kernel": ops.generator_kernel_name(),
+                     "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "note": "2 B stored per entry x entries per launch / CUDA-event "
+                             "time of the generate call on its stream"},
+        "step_ms_min_max": [min(per_step), max(per_step)],
+        "wall_s_timed_region": t_host1 - t_host0,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    if world == 1 and not args.no_scorer:
+        try:
+            line["scorer"] = scorer_figures(torch, ops)
+        except Exception as e:  # secondary figures must not lose the headline
+            line["scorer"] = {"error": repr(e)}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,9 @@ __device__ uint2 g_pix_dhgr[4][1 << 13];
 struct Lut {
   uint8_t s[256];
 };
+struct Lut32 {
+  int32_t s[256];
+};
 
 // Destination tables of one generate call: the local table, or every rank's
 // peer-mapped table (fused generate + all-gather over NVLink), or one NVSwitch
@@ -154,7 +157,7 @@ chain_kernel(Lut lut, Dests dests, uint32_t row_begin, int triangular) {
 
 // edit_distance (make_data_tables.py:92-108) for explicit pixel strings: pairs of
 // `len` nibble-valued pixels, one thread per pair.
-__global__ void string_distance_kernel(Lut lut, const uint8_t* __restrict__ a,
+__global__ void string_distance_kernel(Lut32 lut, const uint8_t* __restrict__ a,
                                        const uint8_t* __restrict__ b, int n_pairs,
                                        int len, int32_t* __restrict__ out) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -326,9 +329,16 @@ extern "C" int iiv_string_distance(const int32_t* h_lut, const uint8_t* d_a,
                                    const uint8_t* d_b, int n_pairs, int len,
                                    int32_t* d_out, void* stream) {
   IIV_REQUIRE(h_lut && d_a && d_b && d_out && n_pairs >= 0 && len >= 0, "bad argument");
-  Lut lut;
-  const int rc = make_lut(h_lut, &lut);
-  if (rc) return rc;
+  // edit_distance(error=True) uses 5x costs (make_data_tables.py:85-86), so the
+  // explicit-string entry point takes any cost that keeps the sum in int32.
+  Lut32 lut;
+  for (int k = 0; k < 256; ++k) {
+    if (h_lut[k] < 0 || (int64_t)h_lut[k] * len > 0x7fffffff) {
+      set_error("substitution cost %d at [%d][%d] out of range", h_lut[k], k >> 4, k & 15);
+      return IIV_E_OVERFLOW;
+    }
+    lut.s[k] = h_lut[k];
+  }
   if (n_pairs == 0) return 0;
   string_distance_kernel<<<(n_pairs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       lut, d_a, d_b, n_pairs, len, d_out);

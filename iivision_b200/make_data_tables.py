@@ -1,0 +1,170 @@
+"""Edit-distance table generation (reference transcoder/make_data_tables.py) on the
+GPU, behind the reference's function names and signatures.
+
+    python -m iivision_b200.make_data_tables        # writes transcoder/data/*.npz
+
+colormath and weighted-levenshtein are not dependencies: the CIE2000 matrix is an
+FP64 device kernel (iiv_lut_cie2000) and the weighted Damerau-Levenshtein
+distances are the table kernels of csrc/iiv_tables.cu.  The reference's ~90
+CPU-minutes (README.md:64-67) become milliseconds of kernel time; what remains is
+the device->host copy and np.savez_compressed.
+"""
+
+import functools
+import os
+from typing import Iterable, Type
+
+import numpy as np
+import torch
+
+from . import colours
+from . import ops
+from . import palette
+from . import screen
+
+PIXEL_CHARS = "0123456789ABCDEF"
+DATA_DIR = "transcoder/data"
+
+
+def pixel_char(i: int) -> str:
+    return PIXEL_CHARS[i]
+
+
+@functools.lru_cache(None)
+def pixel_string(pixels: Iterable[int]) -> str:
+    return "".join(pixel_char(p) for p in pixels)
+
+
+class EditDistanceParams:
+    """Data class for parameters to Damerau-Levenshtein edit distance.
+
+    As in the reference (make_data_tables.py:30-52) the arrays are CLASS
+    attributes that compute_substitute_costs fills in place.
+    """
+
+    # Insertions and deletions make no sense for pixel strings
+    insert_costs = np.ones(128, dtype=np.float64) * 100000
+    delete_costs = np.ones(128, dtype=np.float64) * 100000
+    transpose_costs = np.ones((128, 128), dtype=np.float64)
+    substitute_costs = np.zeros((128, 128), dtype=np.float64)
+    # 5x costs for evaluating other offsets for a content byte (unused upstream)
+    error_substitute_costs = np.zeros((128, 128), dtype=np.float64)
+
+
+def compute_diff_matrix(pal: Type[palette.BasePalette]):
+    """Matrix of int()-truncated CIE2000 delta-E between palette colour pairs,
+    indexed by nominal colour value (device FP64; make_data_tables.py:55-70)."""
+    return ops.lut_cie2000(pal.rgb_by_value())
+
+
+def compute_substitute_costs(pal: Type[palette.BasePalette]):
+    """Compute costs for substituting one colour pixel for another."""
+    edp = EditDistanceParams()
+    diff_matrix = compute_diff_matrix(pal)
+    idx = np.frombuffer(PIXEL_CHARS.encode("ascii"), dtype=np.uint8)
+    # (j, i) is written after (i, j) upstream, so S[c][d] = dm[max, min]; the
+    # matrix is symmetric after truncation so the order is immaterial
+    cost = np.tril(diff_matrix) + np.tril(diff_matrix, -1).T
+    edp.substitute_costs[np.ix_(idx, idx)] = cost
+    edp.error_substitute_costs[np.ix_(idx, idx)] = 5 * cost
+    return edp
+
+
+def _lut16(costs: np.ndarray) -> np.ndarray:
+    idx = np.frombuffer(PIXEL_CHARS.encode("ascii"), dtype=np.uint8)
+    sub = np.asarray(costs)[np.ix_(idx, idx)]
+    lut = sub.astype(np.int32)
+    if not np.array_equal(lut, sub):
+        raise ValueError("substitution costs must be integral")
+    return lut
+
+
+def _check_chain_conditions(edp, n: int, lut: np.ndarray) -> None:
+    """The device kernels evaluate the substitution/transposition chain the full
+    Damerau-Levenshtein DP collapses to when an insert+delete pair can never pay
+    for itself (make_data_tables.py:35-36).  Refuse parameter sets where that does
+    not hold instead of silently computing something else."""
+    idx = np.frombuffer(PIXEL_CHARS.encode("ascii"), dtype=np.uint8)
+    if (min(edp.insert_costs[idx].min(), edp.delete_costs[idx].min())
+            <= n * max(int(lut.max()), 1)):
+        raise ValueError("insert/delete costs too small for the substitution-only "
+                         "collapse; unsupported parameter set")
+    tc = getattr(edp, "transpose_costs", None)
+    if tc is not None and not np.all(np.asarray(tc)[np.ix_(idx, idx)] == 1):
+        raise ValueError("only unit transposition costs are supported")
+    if not np.array_equal(lut, lut.T) or np.diagonal(lut).any():
+        raise ValueError("substitution costs must be symmetric with zero diagonal")
+
+
+def edit_distance(edp: EditDistanceParams, a: str, b: str, error: bool) -> np.float64:
+    """Damerau-Levenshtein edit distance between two pixel strings."""
+    if len(a) != len(b):
+        raise ValueError("pixel strings must have equal length")
+    lut = _lut16(edp.error_substitute_costs if error else edp.substitute_costs)
+    _check_chain_conditions(edp, max(len(a), 1), lut)
+    sa = np.array([[PIXEL_CHARS.index(c) for c in a]], dtype=np.uint8).reshape(1, -1)
+    sb = np.array([[PIXEL_CHARS.index(c) for c in b]], dtype=np.uint8).reshape(1, -1)
+    res = np.float64(ops.string_distance(lut, sa, sb)[0]) if len(a) else np.float64(0)
+    assert (0 <= res < 2 ** 16), res
+    return res
+
+
+def _mode_of(bitmap_cls) -> int:
+    name = getattr(bitmap_cls, "NAME", None)
+    if name not in ops.MODES:
+        raise ValueError("unknown bitmap class %r" % (bitmap_cls,))
+    m = ops.MODES[name]
+    if (int(bitmap_cls.MASKED_BITS) != ops.MASKED_BITS[m]
+            or int(bitmap_cls.MASKED_DOTS) != ops.MASKED_DOTS[m]
+            or list(bitmap_cls.PHASES) != ops.mode_phases(m)):
+        raise ValueError("%s geometry differs from the compiled kernels" % name)
+    return m
+
+
+def compute_edit_distance_device(edp: EditDistanceParams, bitmap_cls,
+                                 layout: int = ops.LAYOUT_TRIANGULAR,
+                                 out: torch.Tensor = None) -> torch.Tensor:
+    """compute_edit_distance leaving the table in HBM (uint16[n_off, 4**bits])."""
+    m = _mode_of(bitmap_cls)
+    lut = _lut16(edp.substitute_costs)
+    _check_chain_conditions(edp, ops.MASKED_DOTS[m], lut)
+    return ops.table_generate(m, lut, layout=layout, out=out)
+
+
+def compute_edit_distance(edp: EditDistanceParams, bitmap_cls: Type[screen.Bitmap],
+                          nominal_colours: Type[colours.NominalColours] = None
+                          ) -> np.ndarray:
+    """Computes edit distance matrix between all pairs of pixel strings.
+
+    Returns the reference's array: uint16[(len(BYTE_MASKS), 4**MASKED_BITS)],
+    entry (i << bits) + j filled for j < i only (make_data_tables.py:156-172).
+    ``nominal_colours`` only validated pixel values upstream and is ignored.
+    """
+    table = compute_edit_distance_device(edp, bitmap_cls, ops.LAYOUT_TRIANGULAR)
+    host = torch.empty(table.shape, dtype=torch.uint16, pin_memory=True)
+    host.copy_(table, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
+def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,
+                       bitmap_cls: Type[screen.Bitmap],
+                       nominal_colours: Type[colours.NominalColours] = None):
+    """Write file containing (D)HGR edit distance matrix for a palette."""
+    dist = compute_edit_distance(edp, bitmap_cls, nominal_colours)
+    data = "%s/%s_palette_%d_edit_distance.npz" % (
+        DATA_DIR, bitmap_cls.NAME, pal.ID.value)
+    np.savez_compressed(data, edit_distance=dist)
+
+
+def main():
+    os.makedirs(DATA_DIR, mode=0o755, exist_ok=True)
+    for p in palette.PALETTES.values():
+        print("Processing palette %s" % p)
+        edp = compute_substitute_costs(p)
+        make_edit_distance(p, edp, screen.HGRBitmap, colours.HGRColours)
+        make_edit_distance(p, edp, screen.DHGRBitmap, colours.DHGRColours)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,11 @@ def mode_id(mode) -> int:
     return int(mode)
 
 
+def mode_phases(mode):
+    """PHASES of the bitmap class (screen.py:645, :919)."""
+    return _lib.mode_info(mode_id(mode))[3]
+
+
 def table_shape(mode):
     m = mode_id(mode)
     return (NUM_OFFSETS[m], 1 << (2 * MASKED_BITS[m]))
@@ -115,6 +120,22 @@ def table_generate(mode, lut, layout=LAYOUT_SYMMETRIC, row_begin=0, row_end=None
     check(lib.iiv_table_generate(m, lut.ctypes.data, _ptr(out), row_begin,
                                  row_end, layout, algo, _stream()))
     return out
+
+
+def launches_per_table_generate() -> int:
+    """Kernels one iiv_table_generate call launches (pixel prologue + generator)."""
+    return 2
+
+
+def generator_kernel_name() -> str:
+    return "chain_kernel"
+
+
+def table_generate_into(mode, lut, layout, row_begin, row_end,
+                        out: torch.Tensor) -> torch.Tensor:
+    """Positional form used by parallel.generate_sharded."""
+    return table_generate(mode, lut, layout=layout, row_begin=row_begin,
+                          row_end=row_end, out=out)
 
 
 def table_generate_scatter(mode, lut, peer_ptrs, rank, row_begin, row_end,

@@ -55,6 +55,10 @@ def lib() -> ctypes.CDLL:
         L.oracle_build_table.argtypes = [
             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
             ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+        L.oracle_build_table_strided.restype = ctypes.c_int64
+        L.oracle_build_table_strided.argtypes = [
+            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32,
+            ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
         L.oracle_symmetrise.argtypes = [ctypes.c_int, ctypes.c_void_p]
         _lib = L
     return _lib
@@ -115,12 +119,13 @@ def chain_distance(a: np.ndarray, b: np.ndarray, lut: np.ndarray) -> int:
 def build_table(mode: str, lut: np.ndarray, row_begin: int = 0,
                 row_end: int = None, faithful: bool = False,
                 triangular: bool = True, out: np.ndarray = None,
-                threads: int = None):
+                threads: int = None, row_step: int = 1):
     """compute_edit_distance restated (make_data_tables.py:111-174).
 
     Returns (table uint16[n_off, 4**bits], entries evaluated).  ``faithful``
     runs the full (n+2)^2 float64 dam_lev per pair; otherwise the exact 1-D
-    recurrence.  Only rows [row_begin, row_end) are filled.
+    recurrence.  Only rows row_begin, row_begin + row_step, ... < row_end are
+    filled.
     """
     bits = MASKED_BITS[mode]
     if row_end is None:
@@ -130,9 +135,9 @@ def build_table(mode: str, lut: np.ndarray, row_begin: int = 0,
     lut = np.ascontiguousarray(lut, dtype=np.int32)
     if threads is not None:
         lib().oracle_set_threads(int(threads))
-    n = lib().oracle_build_table(
+    n = lib().oracle_build_table_strided(
         MODES[mode], lut.ctypes.data, out.ctypes.data, row_begin, row_end,
-        0 if faithful else 1, 1 if triangular else 0)
+        max(1, int(row_step)), 0 if faithful else 1, 1 if triangular else 0)
     return out, int(n)
 
 

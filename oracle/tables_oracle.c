@@ -260,10 +260,12 @@ typedef struct {
   const double *ins, *del, *sub;
   uint16_t* out;
   atomic_llong evaluated;
+  int64_t row_begin, row_step;
 } build_ctx;
 
-static void build_row(int64_t i, void* p) {
+static void build_row(int64_t k, void* p) {
   build_ctx* c = (build_ctx*)p;
+  const int64_t i = c->row_begin + k * c->row_step;
   const int bits = kBits[c->mode], n = kDots[c->mode], noff = kOffsets[c->mode];
   const uint32_t N = 1u << bits;
   uint8_t sa[32], sb[32];
@@ -298,9 +300,10 @@ static void build_row(int64_t i, void* p) {
  * otherwise the full symmetric square.
  * Returns the number of entries evaluated.
  */
-int64_t oracle_build_table(int mode, const int32_t* lut, uint16_t* out,
-                           uint32_t row_begin, uint32_t row_end, int algo,
-                           int triangular) {
+ /* rows row_begin, row_begin + row_step, ... < row_end */
+int64_t oracle_build_table_strided(int mode, const int32_t* lut, uint16_t* out,
+                                   uint32_t row_begin, uint32_t row_end,
+                                   uint32_t row_step, int algo, int triangular) {
   const int bits = kBits[mode], n = kDots[mode], noff = kOffsets[mode];
   const uint32_t N = 1u << bits;
   uint8_t* pix = (uint8_t*)malloc((size_t)noff * N * n);
@@ -319,10 +322,23 @@ int64_t oracle_build_table(int mode, const int32_t* lut, uint16_t* out,
   c.sub = sub;
   c.out = out;
   atomic_init(&c.evaluated, 0);
-  parallel_rows(row_begin, row_end, 4, build_row, &c);
+  if (row_step == 0) row_step = 1;
+  c.row_begin = row_begin;
+  c.row_step = row_step;
+  const int64_t n_rows =
+      row_end > row_begin ? ((int64_t)row_end - row_begin + row_step - 1) / row_step : 0;
+  /* a faithful row is ~10^4 full DPs: hand rows out one at a time */
+  parallel_rows(0, n_rows, algo == 0 ? 1 : 4, build_row, &c);
   free(sub);
   free(pix);
   return (int64_t)atomic_load(&c.evaluated);
+}
+
+int64_t oracle_build_table(int mode, const int32_t* lut, uint16_t* out,
+                           uint32_t row_begin, uint32_t row_end, int algo,
+                           int triangular) {
+  return oracle_build_table_strided(mode, lut, out, row_begin, row_end, 1, algo,
+                                    triangular);
 }
 
 typedef struct {

@@ -1,0 +1,77 @@
+"""CPU, world_size 2 over gloo: the multi-GPU host logic (row-block sharding +
+in-place all-gather of the table, clip-per-rank sharding).  The CUDA generator
+is replaced by the oracle here, purely so the exchange can run without a GPU."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_generate(mode, lut, layout, begin, end, out):
+    from oracle import tables
+    name = {0: "HGR", 1: "DHGR"}[mode]
+    view = out.numpy().view(np.uint16) if out.dtype != torch.uint16 else out.view(torch.int16).numpy().view(np.uint16)
+    tables.build_table(name, lut, begin, end, triangular=(layout == 0), out=view)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from iivision_b200 import parallel
+        from oracle import tables
+        lut = tables.substitution_lut(5)
+        for layout in (1, 0):
+            out = torch.zeros((4, 1 << 26), dtype=torch.int16).view(torch.uint16)
+            parallel.generate_sharded("DHGR", lut, layout=layout, out=out,
+                                      generate_fn=_oracle_generate)
+            want, _ = tables.build_table("DHGR", lut, triangular=(layout == 0))
+            got = out.view(torch.int16).numpy().view(np.uint16)
+            assert np.array_equal(got, want), "layout %d rank %d" % (layout, rank)
+        lo, hi = parallel.shard_range(5, world, rank)
+        got = parallel.gather_clip_outputs(np.arange(lo, hi), 5)
+        if rank == 0:
+            assert np.concatenate(got).tolist() == [0, 1, 2, 3, 4]
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitions():
+    from iivision_b200 import parallel
+    for world in (1, 2, 4, 8):
+        parts = parallel.row_partition(8192, world)
+        assert parts[0][0] == 0 and parts[-1][1] == 8192
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert len({e - b for b, e in parts}) == 1
+    with pytest.raises(ValueError):
+        parallel.row_partition(8192, 3)
+    for n, world in ((64, 8), (5, 2), (3, 4), (0, 2)):
+        spans = [parallel.shard_range(n, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_sharded_table_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=280) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
