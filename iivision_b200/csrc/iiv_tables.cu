@@ -155,6 +155,252 @@ chain_kernel(Lut lut, Dests dests, uint32_t row_begin, int triangular) {
   for (int d = 0; d < dests.n; ++d) *reinterpret_cast<uint4*>(dests.p[d] + at) = v;
 }
 
+// ---- ALGO_TREE: shared-suffix tree over 8x8 tiles ---------------------------------
+// The chain can be run from the last pixel backwards,
+//     F_t = min(F_{t+1} + S[a_t][b_t],  F_{t+2} + 1 if a_t==b_{t+1} && a_{t+1}==b_t),
+// F_n = 0, entry = F_0 (same set of tilings by singles and swapped pairs as the
+// forward form).  The low three bits of a masked value only reach the first
+// kLeaf pixels (HGR: bit 1 -> pixels 0..3, bits 0 and 2 -> pixels 0..1; DHGR: bit k
+// -> pixels 0..k; tests/test_oracle_tables.py::test_low_bits_reach_leaf_pixels_only),
+// so an 8x8 tile of entries (8 consecutive i) x (8 consecutive j) shares
+// F_kLeaf, F_kLeaf+1 and only the leaf pixels are walked per entry, as a tree over
+// the bits each pixel depends on:
+//   HGR : 14 shared steps + 4 x (pixels 3,2) + 64 x (pixels 1,0) = 150 steps / 64
+//   DHGR:  7 shared steps + 4 + 16 + 64                          =  91 steps / 64
+// instead of 18 (10) steps per entry.  A thread owns one j-tile (its strings are
+// decoded once into registers) and walks a chunk of i-tiles whose decoded strings
+// the block stages in shared memory; a warp's 32 j-tiles make each row store
+// 512 contiguous bytes.  A step is: LDS.U8 of S[a][b] (a is warp-uniform, so the
+// 16-byte row is one broadcast wavefront), add, compare of the swap keys, min.
+constexpr int kTreeThreads = 128;
+constexpr int kTilesPerChunk = 16;   // i-tiles (of 8 rows) per block
+
+template <int MODE>
+struct Tree {
+  static constexpr int kLeaf = MODE == IIV_MODE_HGR ? 4 : 3;
+  static constexpr int kSfx = Mode<MODE>::kDots - kLeaf;      // shared pixels
+  static constexpr int kSfxPad = (kSfx + 1) & ~1;
+  // words of decoded i-side strings per tile: {lut row address, swap key} per pixel
+  static constexpr int kTileWords = 2 * kSfxPad + 8 * 2 * 4;
+};
+
+constexpr uint32_t kInf = 0x3fffffffu;
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// One chain step for the two innermost pixels (0 and 1), which carry 85 % of the
+// steps.  row = shared address of S[a_t][0] (16 bytes: a is warp-uniform, lanes
+// differ in b only, so the load is one conflict-free broadcast wavefront);
+// kf = a_t | a_{t+1} << 4; pb = b_t; kr = b_{t+1} | b_t << 4; f1 = F_{t+1};
+// h2 = F_{t+2} + 1.
+__device__ __forceinline__ uint32_t tree_step(uint32_t f1, uint32_t h2, uint32_t row,
+                                              uint32_t kf, uint32_t pb, uint32_t kr) {
+  uint32_t c = f1 + lds_u8(row + pb);
+  if (kf == kr) c = min(c, h2);
+  return c;
+}
+
+// The same step for the outer pixels, where registers matter more than bank
+// conflicts: one per-lane register kr serves as swap key AND as index into the
+// widened table S2[a][kr] = S[a][kr >> 4] (row2 = shared address of S2[a_t][0]).
+__device__ __forceinline__ uint32_t tree_step2(uint32_t f1, uint32_t h2, uint32_t row2,
+                                               uint32_t kf, uint32_t kr) {
+  uint32_t c = f1 + lds_u8(row2 + kr);
+  if (kf == kr) c = min(c, h2);
+  return c;
+}
+
+template <int MODE, bool TRI, bool MULTI>
+__global__ void __launch_bounds__(kTreeThreads, 4)
+tree_kernel(const __grid_constant__ Lut lut, const __grid_constant__ Dests dests,
+            uint32_t row_begin, uint32_t row_end) {
+  using M = Mode<MODE>;
+  using T = Tree<MODE>;
+  constexpr int n = M::kDots, L = T::kLeaf;
+  __shared__ __align__(16) uint8_t S[256];
+  __shared__ __align__(16) uint8_t S2[16 * 256];
+  __shared__ __align__(16) uint32_t idesc[kTilesPerChunk][T::kTileWords];
+
+  const int tid = threadIdx.x;
+  const int o = blockIdx.z;
+  for (int k = tid; k < 256; k += kTreeThreads) S[k] = lut.s[k];
+  for (int k = tid; k < 16 * 256; k += kTreeThreads)
+    S2[k] = lut.s[(k >> 8) * 16 + ((k & 255) >> 4)];
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(S);
+  const uint32_t s2_base = (uint32_t)__cvta_generic_to_shared(S2);
+
+  // ---- i side: decode the chunk's strings into shared memory -----------------------
+  const uint32_t tile0 = (row_begin >> 3) + blockIdx.y * kTilesPerChunk;
+  const uint32_t tile_end = (row_end + 7) >> 3;
+  constexpr int kItems = T::kSfx + 8 * L;            // (pixel) items per tile
+  for (int item = tid; item < kTilesPerChunk * kItems; item += kTreeThreads) {
+    const int tl = item / kItems, k = item - tl * kItems;
+    const uint32_t tile = tile0 + tl;
+    if (tile >= tile_end) continue;
+    int v, t, slot;
+    if (k < T::kSfx) {
+      v = 0; t = L + k; slot = 2 * k;
+    } else {
+      v = (k - T::kSfx) / L; t = (k - T::kSfx) - v * L; slot = 2 * T::kSfxPad + 8 * v + 2 * t;
+    }
+    uint64_t lo; uint32_t hi;
+    load_pixels<MODE>(o, tile * 8 + v, lo, hi);
+    const uint32_t a = pixel_at(lo, hi, t);
+    const uint32_t a1 = t + 1 < n ? pixel_at(lo, hi, t + 1) : 0xffffu;
+    idesc[tl][slot] = t < 2 ? s_base + a * 16 : s2_base + a * 256;
+    idesc[tl][slot + 1] = a | (a1 << 4);
+  }
+
+  // ---- j side: this thread's 8 strings, decoded into registers ----------------------
+  const uint32_t jb = (blockIdx.x * kTreeThreads + tid) * 8;
+  uint32_t sfx_kr[T::kSfx];
+  uint32_t leaf_pb[8][2], leaf_kr[8][L];
+  {
+    uint64_t lo; uint32_t hi;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      load_pixels<MODE>(o, jb + v, lo, hi);
+#pragma unroll
+      for (int t = 0; t < L; ++t) {
+        if (t < 2) leaf_pb[v][t] = pixel_at(lo, hi, t);
+        leaf_kr[v][t] = pixel_at(lo, hi, t + 1) | (pixel_at(lo, hi, t) << 4);
+      }
+      if (v == 0) {
+#pragma unroll
+        for (int k = 0; k < T::kSfx; ++k) {
+          const int t = L + k;
+          sfx_kr[k] = (t + 1 < n ? pixel_at(lo, hi, t + 1) : 0u) | (pixel_at(lo, hi, t) << 4);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  const size_t obase = ((size_t)o << (2 * M::kBits)) + jb;
+  for (int tl = 0; tl < kTilesPerChunk; ++tl) {
+    const uint32_t tile = tile0 + tl;
+    if (tile >= tile_end) break;
+    const uint32_t ib = tile * 8;
+    const uint32_t* d = idesc[tl];
+
+    // One finished row of the tile: mask (reference file layout keeps j < i only;
+    // tiles are 8-aligned on both axes) and store 16 bytes per destination.
+    auto emit = [&](int iv, const uint32_t (&r)[8]) {
+      const uint32_t i = ib + iv;
+      if (i < row_begin || i >= row_end) return;
+      uint4 v = make_uint4(r[0] | (r[1] << 16), r[2] | (r[3] << 16), r[4] | (r[5] << 16),
+                           r[6] | (r[7] << 16));
+      if (TRI && jb >= ib) {
+        if (jb > ib) {
+          v = make_uint4(0, 0, 0, 0);
+        } else {
+          v.x &= (0 < iv ? 0xffffu : 0u) | (1 < iv ? 0xffff0000u : 0u);
+          v.y &= (2 < iv ? 0xffffu : 0u) | (3 < iv ? 0xffff0000u : 0u);
+          v.z &= (4 < iv ? 0xffffu : 0u) | (5 < iv ? 0xffff0000u : 0u);
+          v.w &= (6 < iv ? 0xffffu : 0u) | (7 < iv ? 0xffff0000u : 0u);
+        }
+      }
+      const size_t at = obase + ((size_t)i << M::kBits);
+      if (MULTI) {
+        for (int dd = 0; dd < dests.n; ++dd)
+          *reinterpret_cast<uint4*>(dests.p[dd] + at) = v;
+      } else {
+        *reinterpret_cast<uint4*>(dests.p[0] + at) = v;
+      }
+    };
+
+    // triangular layout: the whole warp lies above the diagonal -> zeros only
+    if (TRI && __all_sync(0xffffffffu, jb >= ib + 8)) {
+      const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int iv = 0; iv < 8; ++iv) emit(iv, z);
+      continue;
+    }
+
+    // shared suffix: pixels n-1 .. L
+    uint32_t f1, f2;    // F_{t+1}, F_{t+2}
+    {
+      const uint2 a = *reinterpret_cast<const uint2*>(d + 2 * (T::kSfx - 1));
+      f1 = lds_u8(a.x + sfx_kr[T::kSfx - 1]);   // last pixel: no swap partner
+      f2 = 0;
+    }
+#pragma unroll
+    for (int k = T::kSfx - 2; k >= 0; --k) {
+      const uint2 a = *reinterpret_cast<const uint2*>(d + 2 * k);
+      const uint32_t f = tree_step2(f1, f2 + 1, a.x, a.y, sfx_kr[k]);
+      f2 = f1;
+      f1 = f;
+    }
+    const uint32_t* leaf = d + 2 * T::kSfxPad;     // [variant][pixel]{row, kf}
+    if (MODE == IIV_MODE_HGR) {
+      // pixels 3, 2 depend on bit 1 only
+      uint32_t F2v[2][2], H3v[2][2], H2v[2][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const uint4 a23 = *reinterpret_cast<const uint4*>(leaf + 8 * (2 * mi) + 4);
+#pragma unroll
+        for (int mj = 0; mj < 2; ++mj) {
+          const uint32_t f3 = tree_step2(f1, f2 + 1, a23.z, a23.w, leaf_kr[2 * mj][3]);
+          F2v[mi][mj] = tree_step2(f3, f1 + 1, a23.x, a23.y, leaf_kr[2 * mj][2]);
+          H3v[mi][mj] = f3 + 1;
+          H2v[mi][mj] = F2v[mi][mj] + 1;
+        }
+      }
+#pragma unroll
+      for (int iv = 0; iv < 8; ++iv) {
+        const int mi = (iv >> 1) & 1;
+        const uint4 a01 = *reinterpret_cast<const uint4*>(leaf + 8 * iv);
+        uint32_t r[8];
+#pragma unroll
+        for (int jv = 0; jv < 8; ++jv) {
+          const int mj = (jv >> 1) & 1;
+          const uint32_t g1 = tree_step(F2v[mi][mj], H3v[mi][mj], a01.z, a01.w,
+                                        leaf_pb[jv][1], leaf_kr[jv][1]);
+          r[jv] = tree_step(g1, H2v[mi][mj], a01.x, a01.y, leaf_pb[jv][0], leaf_kr[jv][0]);
+        }
+        emit(iv, r);
+      }
+    } else {
+      // pixel 2 <- bit 2; pixel 1 <- bits 1,2; pixel 0 <- bits 0,1,2
+      uint32_t F2v[2][2], H2v[2][2];
+#pragma unroll
+      for (int i2 = 0; i2 < 2; ++i2) {
+        const uint2 a2 = *reinterpret_cast<const uint2*>(leaf + 8 * (4 * i2) + 4);
+#pragma unroll
+        for (int j2 = 0; j2 < 2; ++j2) {
+          F2v[i2][j2] = tree_step2(f1, f2 + 1, a2.x, a2.y, leaf_kr[4 * j2][2]);
+          H2v[i2][j2] = F2v[i2][j2] + 1;
+        }
+      }
+      const uint32_t h3 = f1 + 1;
+#pragma unroll
+      for (int i12 = 0; i12 < 4; ++i12) {
+        const uint2 a1 = *reinterpret_cast<const uint2*>(leaf + 8 * (2 * i12) + 2);
+        uint32_t F1v[4];
+#pragma unroll
+        for (int j12 = 0; j12 < 4; ++j12)
+          F1v[j12] = tree_step(F2v[i12 >> 1][j12 >> 1], h3, a1.x, a1.y,
+                               leaf_pb[2 * j12][1], leaf_kr[2 * j12][1]);
+#pragma unroll
+        for (int i0 = 0; i0 < 2; ++i0) {
+          const int iv = 2 * i12 + i0;
+          const uint2 a0 = *reinterpret_cast<const uint2*>(leaf + 8 * iv);
+          uint32_t r[8];
+#pragma unroll
+          for (int jv = 0; jv < 8; ++jv)
+            r[jv] = tree_step(F1v[jv >> 1], H2v[i12 >> 1][jv >> 2], a0.x, a0.y,
+                              leaf_pb[jv][0], leaf_kr[jv][0]);
+          emit(iv, r);
+        }
+      }
+    }
+  }
+}
+
 // edit_distance (make_data_tables.py:92-108) for explicit pixel strings: pairs of
 // `len` nibble-valued pixels, one thread per pair.
 __global__ void string_distance_kernel(Lut32 lut, const uint8_t* __restrict__ a,
@@ -218,13 +464,28 @@ int generate(const Lut& lut, const Dests& dests, uint32_t row_begin,
   if (row_begin == row_end) return 0;
   pixel_prologue<MODE><<<dim3(N / 256, M::kOffsets), 256, 0, st>>>();
   IIV_LAUNCH_CHECK("pixel_prologue");
-  (void)algo;
-  const uint32_t rows = row_end - row_begin;
-  // gridDim.y <= 65535 holds: rows <= 16384.
-  dim3 grid(N / (kChainThreads * kChainPerThread), rows, M::kOffsets);
-  chain_kernel<MODE><<<grid, kChainThreads, 0, st>>>(
-      lut, dests, row_begin, layout == IIV_LAYOUT_TRIANGULAR);
-  IIV_LAUNCH_CHECK("chain_kernel");
+  if (algo == IIV_ALGO_CHAIN) {
+    const uint32_t rows = row_end - row_begin;
+    // gridDim.y <= 65535 holds: rows <= 16384.
+    dim3 grid(N / (kChainThreads * kChainPerThread), rows, M::kOffsets);
+    chain_kernel<MODE><<<grid, kChainThreads, 0, st>>>(
+        lut, dests, row_begin, layout == IIV_LAYOUT_TRIANGULAR);
+    IIV_LAUNCH_CHECK("chain_kernel");
+    return 0;
+  }
+  const uint32_t tiles = ((row_end + 7) >> 3) - (row_begin >> 3);
+  dim3 grid(N / (kTreeThreads * 8), (tiles + kTilesPerChunk - 1) / kTilesPerChunk,
+            M::kOffsets);
+  const bool tri = layout == IIV_LAYOUT_TRIANGULAR, multi = dests.n > 1;
+  if (tri && multi)
+    tree_kernel<MODE, true, true><<<grid, kTreeThreads, 0, st>>>(lut, dests, row_begin, row_end);
+  else if (tri)
+    tree_kernel<MODE, true, false><<<grid, kTreeThreads, 0, st>>>(lut, dests, row_begin, row_end);
+  else if (multi)
+    tree_kernel<MODE, false, true><<<grid, kTreeThreads, 0, st>>>(lut, dests, row_begin, row_end);
+  else
+    tree_kernel<MODE, false, false><<<grid, kTreeThreads, 0, st>>>(lut, dests, row_begin, row_end);
+  IIV_LAUNCH_CHECK("tree_kernel");
   return 0;
 }
 

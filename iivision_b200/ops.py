@@ -128,7 +128,7 @@ def launches_per_table_generate() -> int:
 
 
 def generator_kernel_name() -> str:
-    return "chain_kernel"
+    return "tree_kernel"
 
 
 def table_generate_into(mode, lut, layout, row_begin, row_end,

@@ -50,6 +50,38 @@ def test_full_table_bit_exact(ops, oracle_luts, mode, pid):
 
 
 @pytest.mark.parametrize("mode", ["DHGR", "HGR"])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_tree_kernel_equals_chain_kernel(ops, oracle_luts, mode, layout):
+    """The shared-suffix tree generator against the one-chain-per-entry kernel,
+    with an adversarial LUT (zeros off the diagonal, values up to 255)."""
+    import torch
+    from iivision_b200._lib import ALGO_CHAIN, ALGO_TREE
+    rng = np.random.default_rng(11)
+    lut = rng.integers(0, 256, size=(16, 16)).astype(np.int32)
+    lut = np.minimum(lut, lut.T)
+    lut[rng.random((16, 16)) < 0.15] = 0
+    lut = np.minimum(lut, lut.T)
+    np.fill_diagonal(lut, 0)
+    for table_lut in (oracle_luts[5], lut):
+        a = ops.table_generate(mode, table_lut, layout=layout, algo=ALGO_CHAIN)
+        b = ops.table_generate(mode, table_lut, layout=layout, algo=ALGO_TREE)
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+
+
+def test_row_ranges_unaligned(ops, oracle_luts):
+    """Row ranges that do not fall on the generator's 8-row tiles."""
+    import torch
+    lut = oracle_luts[0]
+    for layout in (0, 1):
+        full = ops.table_generate("HGR", lut, layout=layout)
+        out = torch.zeros_like(full)
+        for a, b in ((0, 3), (3, 8), (8, 9), (9, 1023), (1023, 1025), (1025, 16381),
+                     (16381, 16384)):
+            ops.table_generate("HGR", lut, layout=layout, row_begin=a, row_end=b, out=out)
+        assert torch.equal(out.view(torch.int16), full.view(torch.int16))
+
+
+@pytest.mark.parametrize("mode", ["DHGR", "HGR"])
 def test_symmetrise_and_symmetric_layout(ops, oracle_luts, oracle_tables, mode):
     lut = oracle_luts[5]
     tri = ops.table_generate(mode, lut, layout=ops.LAYOUT_TRIANGULAR)

@@ -157,3 +157,19 @@ def test_hgr_ntsc_known_answers(oracle_tables):
     assert t.max() == 1818
     sq = t[1].reshape(16384, 16384)
     assert np.array_equal(sq[:2048, :2048], sq[:2048, :2048].T)
+
+
+@pytest.mark.parametrize("mode,leaf", [("HGR", 4), ("DHGR", 3)])
+def test_low_bits_reach_leaf_pixels_only(mode, leaf):
+    """The structural fact the tree generator (csrc/iiv_tables.cu) relies on: the low
+    three bits of a masked value only influence the first `leaf` pixels, and in the
+    pattern the kernel's tree walks."""
+    pix = tables.all_pixel_strings(mode)
+    v = np.arange(1 << tables.MASKED_BITS[mode])
+    n = tables.MASKED_DOTS[mode]
+    want = ({0: {0, 1}, 1: {0, 1, 2, 3}, 2: {0, 1}} if mode == "HGR"
+            else {0: {0}, 1: {0, 1}, 2: {0, 1, 2}})
+    for o in range(pix.shape[0]):
+        for bit in range(3):
+            dep = {t for t in range(n) if (pix[o][v, t] != pix[o][v ^ (1 << bit), t]).any()}
+            assert dep <= want[bit] and max(dep) < leaf, (mode, o, bit, dep)
