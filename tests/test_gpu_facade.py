@@ -1,0 +1,201 @@
+"""GPU: the reference-named Python facades (make_data_tables / screen / video)
+against fixtures produced by the unmodified reference and against the oracle."""
+
+import contextlib
+import io
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from iivision_b200 import colours, make_data_tables, palette, screen, video, video_mode
+    import types
+    return types.SimpleNamespace(colours=colours, mdt=make_data_tables, palette=palette,
+                                 screen=screen, video=video, video_mode=video_mode)
+
+
+class _Grabber:
+    input_frame_rate = 30
+
+
+def test_make_data_tables_facade(mods, oracle_luts):
+    from oracle import tables
+    for pal in (mods.palette.NTSCPalette, mods.palette.IIGSPalette):
+        pid = pal.ID.value
+        assert np.array_equal(mods.mdt.compute_diff_matrix(pal), oracle_luts[pid])
+        edp = mods.mdt.compute_substitute_costs(pal)
+        assert edp.substitute_costs[ord("0"), ord("F")] == 99
+        assert edp.error_substitute_costs[ord("3"), ord("C")] == 5 * oracle_luts[pid][3, 12]
+        assert edp.substitute_costs[ord("A"), ord("a")] == 0       # only '0'..'F' filled
+    edp = mods.mdt.compute_substitute_costs(mods.palette.NTSCPalette)
+    got = mods.mdt.compute_edit_distance(edp, mods.screen.DHGRBitmap, mods.colours.DHGRColours)
+    want, _ = tables.build_table("DHGR", oracle_luts[5], triangular=True)
+    assert got.dtype == np.uint16 and got.shape == want.shape
+    assert np.array_equal(got, want)
+    # edit_distance on explicit strings, both cost sets (make_data_tables.py:92-108)
+    a, b = "0123456789", "1023456798"
+    lut = oracle_luts[5]
+    na = np.array([int(c, 16) for c in a], np.uint8)
+    nb = np.array([int(c, 16) for c in b], np.uint8)
+    assert mods.mdt.edit_distance(edp, a, b, error=False) == tables.chain_distance(na, nb, lut)
+    assert mods.mdt.edit_distance(edp, a, b, error=True) == tables.chain_distance(na, nb, 5 * lut)
+    assert mods.mdt.pixel_string((1, 2, 15)) == "12F"
+    # parameter sets the collapse does not cover are refused, not mis-computed
+    bad = mods.mdt.EditDistanceParams()
+    saved = bad.insert_costs.copy()
+    try:
+        type(bad).insert_costs[:] = 10
+        with pytest.raises(ValueError):
+            mods.mdt.compute_edit_distance(bad, mods.screen.DHGRBitmap)
+    finally:
+        type(bad).insert_costs[:] = saved
+
+
+def test_make_edit_distance_writes_reference_file(mods, oracle_luts, tmp_path, monkeypatch):
+    """npz name/key/layout as the reference writes them; the loader symmetrises it."""
+    from oracle import tables
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("transcoder/data")
+    pal = mods.palette.IIGSPalette
+    edp = mods.mdt.compute_substitute_costs(pal)
+    mods.mdt.make_edit_distance(pal, edp, mods.screen.DHGRBitmap, mods.colours.DHGRColours)
+    path = "transcoder/data/DHGR_palette_0_edit_distance.npz"
+    tri = np.load(path)["edit_distance"]
+    want, _ = tables.build_table("DHGR", oracle_luts[0], triangular=True)
+    assert np.array_equal(tri, want)
+    mods.screen.DHGRBitmap.edit_distances_device.cache_clear()
+    mods.screen.DHGRBitmap.edit_distances.cache_clear()
+    try:
+        sym = mods.screen.DHGRBitmap.edit_distances(mods.palette.Palette.IIGS)   # from the file
+        assert np.array_equal(sym, tables.symmetrise("DHGR", want))
+    finally:
+        mods.screen.DHGRBitmap.edit_distances_device.cache_clear()
+        mods.screen.DHGRBitmap.edit_distances.cache_clear()
+
+
+@pytest.mark.parametrize("mode", ["HGR", "DHGR"])
+def test_screen_facade(mods, mode):
+    g = np.load(os.path.join(GOLDEN, "scorer_%s.npz" % mode.lower()))
+    s = mods.screen
+    fr = g["frames"]
+
+    def bitmap(k):
+        mm = s.MemoryMap(screen_page=1, page_offset=fr[k, 0].copy())
+        if mode == "DHGR":
+            return s.DHGRBitmap(palette=mods.palette.Palette.NTSC, main_memory=mm,
+                                aux_memory=s.MemoryMap(1, fr[k, 1].copy()))
+        return s.HGRBitmap(palette=mods.palette.Palette.NTSC, main_memory=mm)
+    src, tgt = bitmap(0), bitmap(1)
+    cls = type(src)
+    assert np.array_equal(src.packed, g["src_packed"])
+    assert np.array_equal(tgt.packed, g["tgt_packed"])
+    for o in range(len(cls.BYTE_MASKS)):
+        assert np.array_equal(cls.mask_and_shift_data(g["words"], o), g["mask_shift"][o])
+        assert cls.mask_and_shift_data(g["words"][0, 0], o) == g["mask_shift"][o][0, 0]
+        for k, v in enumerate(g["values"]):
+            assert np.array_equal(cls.masked_update(o, g["words"], np.uint8(v)),
+                                  g["masked_update"][o, k])
+    for tag in (("main", "aux") if mode == "DHGR" else ("main",)):
+        is_aux = tag == "aux"
+        dw = tgt.diff_weights(src, is_aux)
+        assert dw.dtype == np.int32 and np.array_equal(dw, g["diff_weights_" + tag])
+        for (page, content), want in zip(g["delta_cases_" + tag], g["delta_" + tag]):
+            got = tgt.compute_delta_page(int(page), np.uint8(content), dw[page, :], is_aux)
+            assert np.array_equal(got, want)
+        for bo, page, off, content, want in g["pair_difference_" + tag]:
+            assert int(tgt.byte_pair_difference(int(bo), tgt.packed[page, off // 2],
+                                                np.uint8(content))) == want
+    for page, off, is_aux, val in g["apply_stores"][:40]:
+        src.apply(int(page), int(off), bool(is_aux), np.uint8(val))
+    src.apply_many([tuple(int(x) for x in st) for st in g["apply_stores"][40:]])
+    assert np.array_equal(src.packed, g["apply_packed"])
+    assert np.array_equal(src.main_memory.page_offset, g["apply_main"])
+    src._check_consistency()
+    assert np.array_equal(s.SCREEN_HOLES.sum(), 512)
+    with pytest.raises(ValueError):
+        s.MemoryMap(screen_page=3)
+    with pytest.raises(ValueError):
+        s.MemoryMap(screen_page=1, page_offset=np.zeros((3, 3), np.uint8))
+
+
+@pytest.mark.parametrize("name", ["dhgr_sparse", "hgr_full"])
+@pytest.mark.parametrize("speculate", [None, 100])
+def test_video_facade_streams(mods, name, speculate):
+    """Video.encode_frame pulled like Movie.encode pulls it (new generator per segment,
+    old one abandoned), against the reference's own opcode stream."""
+    g = np.load(os.path.join(GOLDEN, "stream_%s.npz" % name))
+    mode = str(g["mode"])
+    seed = int(g["rng_seed"])
+    vm = getattr(mods.video_mode.VideoMode, mode)
+    random.seed(seed)
+    np.random.seed(seed)
+    v = mods.video.Video(_Grabber(), ticks_per_second=14700., mode=vm,
+                         palette=mods.palette.Palette.NTSC, speculate=speculate)
+    frames = g["frames"]
+    got, sims = [], []
+    op_seq = None
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        for frame, is_aux, budget in g["segments"]:
+            mm = mods.screen.MemoryMap(1, frames[frame, 0].copy())
+            if mode == "DHGR":
+                tgt = mods.screen.DHGRBitmap(palette=mods.palette.Palette.NTSC, main_memory=mm,
+                                             aux_memory=mods.screen.MemoryMap(1, frames[frame, 1].copy()))
+            else:
+                tgt = mods.screen.HGRBitmap(palette=mods.palette.Palette.NTSC, main_memory=mm)
+            op_seq = v.encode_frame(tgt, is_aux=bool(is_aux))     # drops the previous generator
+            for _ in range(budget):
+                page, content, offs = next(op_seq)
+                got.append([page, content] + list(offs))
+        op_seq.close()
+    assert np.array_equal(np.array(got, np.uint8), g["opcodes"])
+    sims = [float(line.split()[1]) for line in out.getvalue().splitlines()]
+    assert np.allclose(sims, g["similarity"], atol=1e-6)
+    assert np.array_equal(v.pixelmap.packed, g["packed"])
+    assert np.array_equal(v.memory_map.page_offset, g["main"])
+    assert np.array_equal(v.update_priority, g["priority_main"])
+    if mode == "DHGR":
+        assert np.array_equal(v.aux_memory_map.page_offset, g["aux"])
+        assert np.array_equal(v.aux_update_priority, g["priority_aux"])
+    # the process-global generators sit exactly where the reference left them
+    assert [random.getrandbits(32) for _ in range(4)] == g["next_python_words"].tolist()
+    assert np.random.randint(0, 256, size=4).tolist() == g["next_numpy_bytes"].tolist()
+
+
+def test_video_sync_mid_generator(mods, oracle_tables):
+    """sync() materialises the state after exactly the opcodes pulled so far."""
+    from iivision_b200 import synth
+    from oracle import scorer
+    frames = synth.synthetic_frames("DHGR", 1, 0.4, seed=9)
+    random.seed(3)
+    np.random.seed(3)
+    v = mods.video.Video(_Grabber(), 14700., mode=mods.video_mode.VideoMode.DHGR)
+    ov = scorer.OracleVideo("DHGR", oracle_tables("DHGR"), py_rng=random.Random(3),
+                            np_rng=np.random.RandomState(3))
+    tgt = mods.screen.DHGRBitmap(palette=mods.palette.Palette.NTSC,
+                                 main_memory=mods.screen.MemoryMap(1, frames[0, 0].copy()),
+                                 aux_memory=mods.screen.MemoryMap(1, frames[0, 1].copy()))
+    otgt = ov.target_bitmap(frames[0, 0], frames[0, 1])
+    with contextlib.redirect_stdout(io.StringIO()):
+        seq, oseq = v.encode_frame(tgt, False), ov.encode_frame(otgt, False)
+        for k in range(37):
+            a, b = next(seq), next(oseq)
+            assert (a[0], a[1], a[2]) == (int(b[0]), int(b[1]), [int(x) for x in b[2]])
+        v.sync()
+        assert np.array_equal(v.memory_map.page_offset, ov.main)
+        assert np.array_equal(v.pixelmap.packed, ov.pixelmap.packed)
+        assert np.array_equal(v.update_priority, ov.update_priority)
+        for k in range(400):       # beyond the speculated budget: re-run with doubling
+            a, b = next(seq), next(oseq)
+            assert (a[0], a[1], a[2]) == (int(b[0]), int(b[1]), [int(x) for x in b[2]])
+        seq.close()
+    assert np.array_equal(v.memory_map.page_offset, ov.main)
+    assert np.array_equal(v.update_priority, ov.update_priority)
+    assert v.tick(0) and not v.tick(1) and v.tick(490)
