@@ -138,7 +138,14 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, exchange="fused_peer"):
+    how = ""
+    if n_gpus > 1:
+        how = {"nccl": " + in-place NCCL all-gather",
+               "fused_peer": " + exchange fused into the generator (stores to every "
+                             "rank's peer-mapped table over NVLink)",
+               "fused_mc": " + exchange fused into the generator (multimem.st through "
+                           "the NVSwitch multicast mapping)"}[exchange]
     return {
         "workload": "HGR NTSC edit-distance table (make_data_tables.compute_edit_distance): "
                     "2 offsets x 2^28 uint16 entries = 1 GiB, 18-pixel strings",
@@ -146,8 +153,7 @@ def workload_config(n_gpus):
                   "lower-triangular array for e2e",
         "entries_per_step": ENTRIES,
         "l2": "each step writes 1 GiB (> 126 MB L2); no explicit flush",
-        "parallelism": "rows sharded over %d GPU(s)%s" % (
-            n_gpus, " + in-place NCCL all-gather" if n_gpus > 1 else ""),
+        "parallelism": "rows sharded over %d GPU(s)%s" % (n_gpus, how),
     }
 
 
@@ -305,11 +311,20 @@ def run_ours(args, rank, world, local_rank):
     table = torch.empty(ops.table_shape(MODE), dtype=torch.uint16, device="cuda")
     stream = torch.cuda.current_stream()
 
+    exchange = os.environ.get("IIV_EXCHANGE", "fused_peer")   # fused_peer | fused_mc | nccl
+
+    def sharded_step(how):
+        if how == "nccl":
+            parallel.generate_sharded(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
+        else:
+            parallel.generate_sharded_fused(MODE, lut, layout=ops.LAYOUT_SYMMETRIC,
+                                            multicast=(how == "fused_mc"))
+
     def step():
         if world == 1:
             ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
         else:
-            parallel.generate_sharded(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
+            sharded_step(exchange)
 
     def barrier():
         if world > 1:
@@ -351,6 +366,31 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     value = ENTRIES * args.steps / (total_ms * 1e-3)
+
+    alt = None
+    if world > 1:
+        # the other exchanges, for the record (same K, same barriers)
+        alt = []
+        for other in ("fused_peer", "fused_mc", "nccl"):
+            if other == exchange:
+                continue
+            try:
+                for _ in range(3):
+                    sharded_step(other)
+            except RuntimeError as e:       # e.g. no multicast on this fabric
+                alt.append({"exchange": other, "unavailable": str(e)[:80]})
+                continue
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(args.steps):
+                sharded_step(other)
+            a1.record(stream)
+            barrier()
+            t = torch.tensor([a0.elapsed_time(a1)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            alt.append({"exchange": other, "ms_per_step": float(t.item()) / args.steps,
+                        "value": ENTRIES * args.steps / (float(t.item()) * 1e-3)})
 
     # kernel-only timing for the roofline: the generator kernel(s) of this rank's rows
     rows = parallel.row_partition(1 << BITS, world)[rank]
@@ -416,7 +456,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic (palette constants; no external data)",
-        "config": workload_config(world),
+        "config": workload_config(world, exchange),
         "clocks": clocks,
         "e2e": {"value": ENTRIES * e2e_steps / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": 16 * 3 + 256 * 4,
@@ -436,6 +476,8 @@ def run_ours(args, rank, world, local_rank):
         "step_ms_min_max": [min(per_step), max(per_step)],
         "wall_s_timed_region": t_host1 - t_host0,
     }
+    if alt is not None:
+        line["alt_exchange"] = alt
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     if world == 1 and not args.no_scorer:

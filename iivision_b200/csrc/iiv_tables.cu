@@ -36,7 +36,17 @@ constexpr int kMaxDests = 8;
 struct Dests {
   uint16_t* p[kMaxDests];
   int n;
+  int multicast;  // p[0] is an NVSwitch multicast mapping: one multimem.st reaches all
 };
+
+// 16-byte store through a multicast (multimem) address: the switch replicates it
+// into every member GPU's copy of the buffer.
+__device__ __forceinline__ void multimem_st_v4(uint16_t* addr, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr),
+               "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+               "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
 
 template <int MODE>
 __global__ void pixel_prologue() {
@@ -306,8 +316,12 @@ tree_kernel(const __grid_constant__ Lut lut, const __grid_constant__ Dests dests
       }
       const size_t at = obase + ((size_t)i << M::kBits);
       if (MULTI) {
-        for (int dd = 0; dd < dests.n; ++dd)
-          *reinterpret_cast<uint4*>(dests.p[dd] + at) = v;
+        if (dests.multicast) {
+          multimem_st_v4(dests.p[0] + at, v);
+        } else {
+          for (int dd = 0; dd < dests.n; ++dd)
+            *reinterpret_cast<uint4*>(dests.p[dd] + at) = v;
+        }
       } else {
         *reinterpret_cast<uint4*>(dests.p[0] + at) = v;
       }
@@ -476,7 +490,7 @@ int generate(const Lut& lut, const Dests& dests, uint32_t row_begin,
   const uint32_t tiles = ((row_end + 7) >> 3) - (row_begin >> 3);
   dim3 grid(N / (kTreeThreads * 8), (tiles + kTilesPerChunk - 1) / kTilesPerChunk,
             M::kOffsets);
-  const bool tri = layout == IIV_LAYOUT_TRIANGULAR, multi = dests.n > 1;
+  const bool tri = layout == IIV_LAYOUT_TRIANGULAR, multi = dests.n > 1 || dests.multicast;
   if (tri && multi)
     tree_kernel<MODE, true, true><<<grid, kTreeThreads, 0, st>>>(lut, dests, row_begin, row_end);
   else if (tri)
@@ -553,7 +567,7 @@ extern "C" int iiv_table_generate(int mode, const int32_t* h_lut,
                                   uint32_t row_end, int layout, int algo,
                                   void* stream) {
   IIV_REQUIRE(h_lut && d_table, "null pointer");
-  Dests dests;
+  Dests dests = {};
   dests.n = 1;
   dests.p[0] = d_table;
   return generate_any(mode, h_lut, dests, row_begin, row_end, layout, algo, stream);
@@ -568,9 +582,10 @@ extern "C" int iiv_table_generate_scatter(int mode, const int32_t* h_lut,
   IIV_REQUIRE(h_lut, "null pointer");
   IIV_REQUIRE(n_ranks >= 1 && n_ranks <= kMaxDests && rank >= 0 && rank < n_ranks,
               "bad rank %d of %d", rank, n_ranks);
-  Dests dests;
+  Dests dests = {};
   if (d_multicast_table) {
     dests.n = 1;
+    dests.multicast = 1;
     dests.p[0] = d_multicast_table;
   } else {
     IIV_REQUIRE(h_peer_tables, "null pointer");

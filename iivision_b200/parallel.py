@@ -84,6 +84,50 @@ def generate_sharded(mode, lut, layout: int = _lib.LAYOUT_SYMMETRIC,
     return out
 
 
+_symm_cache = {}
+
+
+def symmetric_table(mode, group=None):
+    """(table, handle): a uint16[n_off, 4**bits] table in NVLink peer-mapped
+    (symmetric) memory, allocated and rendezvous-ed once per (mode, group)."""
+    import torch.distributed._symmetric_memory as symm
+    m = _mode_id(mode)
+    group = group if group is not None else dist.group.WORLD
+    key = (m, group.group_name)
+    if key not in _symm_cache:
+        bits, n_off = MASKED_BITS[m], NUM_OFFSETS[m]
+        buf = symm.empty((n_off, 1 << (2 * bits)), dtype=torch.int16,
+                         device=torch.device("cuda", torch.cuda.current_device()))
+        hdl = symm.rendezvous(buf, group)
+        _symm_cache[key] = (buf.view(torch.uint16), hdl)
+    return _symm_cache[key]
+
+
+def generate_sharded_fused(mode, lut, layout: int = _lib.LAYOUT_SYMMETRIC, group=None,
+                           multicast: Optional[bool] = None) -> torch.Tensor:
+    """compute_edit_distance sharded by row blocks with the exchange fused into
+    the generator: every rank's kernel stores each finished 16-byte run straight
+    into ALL ranks' tables over NVLink (peer-mapped pointers), or once through the
+    NVSwitch multicast mapping (multimem.st), so no separate collective runs.
+    Returns this rank's full table (symmetric-memory backed, reused across calls).
+    """
+    from . import ops
+    m = _mode_id(mode)
+    table, hdl = symmetric_table(m, group)
+    world, rank = hdl.world_size, hdl.rank
+    begin, end = row_partition(1 << MASKED_BITS[m], world, layout)[rank]
+    mc = 0
+    if multicast is None or multicast:
+        mc = int(hdl.multicast_ptr or 0)      # 0 when the fabric has no multicast
+        if multicast and not mc:
+            raise RuntimeError("NVSwitch multicast is not available for this allocation")
+    hdl.barrier(channel=0)        # peers have finished reading the previous contents
+    ops.table_generate_scatter(m, lut, [int(p) for p in hdl.buffer_ptrs], rank, begin, end,
+                               layout=layout, multicast_ptr=mc)
+    hdl.barrier(channel=1)        # every rank's stores have landed everywhere
+    return table
+
+
 def gather_clip_outputs(local: np.ndarray, n_clips: int, group=None) -> Optional[List[np.ndarray]]:
     """Host-side gather of per-clip opcode buffers to rank 0 (not on the timed
     data path: clips are independent)."""
