@@ -331,7 +331,7 @@ def encode_clips(mode, states: torch.Tensor, target_mem: torch.Tensor,
 
     target_mem uint8[n_clips, n_frames, banks, 32, 256]; target_packed
     int64[n_clips, n_frames, 32, 128].  Returns (opcodes uint8[n_clips,
-    total_budget, 8], seg_info int64[n_clips, n_segments, 4])."""
+    total_budget, 8], seg_info int64[n_clips, n_segments, 8])."""
     m = mode_id(mode)
     segs = np.ascontiguousarray(segments, dtype=np.int32).reshape(-1, 3)
     n_clips, n_frames = target_mem.shape[0], target_mem.shape[1]
@@ -346,7 +346,7 @@ def encode_clips(mode, states: torch.Tensor, target_mem: torch.Tensor,
     if opcodes is None:
         opcodes = torch.empty((n_clips, total, 8), dtype=torch.uint8, device="cuda")
     if seg_info is None:
-        seg_info = torch.empty((n_clips, segs.shape[0], 4), dtype=torch.int64,
+        seg_info = torch.zeros((n_clips, segs.shape[0], 8), dtype=torch.int64,
                                device="cuda")
     check(lib.iiv_encode_clips(
         m, n_clips, _ptr(states), STATE_BYTES, _ptr(target_mem),

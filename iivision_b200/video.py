@@ -124,8 +124,11 @@ class Video:
         mt_py = field(ops.F_MT_PY, torch.int32, (640,)).view(np.uint32)[:625]
         np.random.set_state(ops.mt_to_numpy(mt_np))
         random.setstate(ops.mt_to_python(mt_py))
-        if int(field(ops.F_FLAGS, torch.int32, (8,))[2]) & 1:
+        flags = int(field(ops.F_FLAGS, torch.int32, (8,))[2])
+        if flags & 1:
             raise AssertionError("DHGR content byte with bit 7 set")   # video.py:135-137
+        if flags & ~1:
+            raise RuntimeError("encoder kernel internal error %#x" % flags)
 
     # -- encode_frame ------------------------------------------------------------------------
     def encode_frame(self, target: screen.Bitmap, is_aux: bool

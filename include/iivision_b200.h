@@ -197,9 +197,11 @@ int iiv_clip_state_layout(size_t* offsets8);
  *   d_table          symmetric table of the mode
  *   d_opcodes        uint8[n_clips][sum(budget)][8]: page+32, content, o0..o3,
  *                    flag (1 = real opcode, 0 = out-of-work padding), 0
- *   d_seg_info       int64[n_clips][n_segments][4]: real opcodes emitted,
+ *   d_seg_info       int64[n_clips][n_segments][8]: real opcodes emitted,
  *                    sum of update_priority before the segment (video.py:90),
- *                    numpy-stream words drawn, python-stream words drawn
+ *                    numpy-stream words drawn, python-stream words drawn, then
+ *                    tracing counters in SM cycles: score+heapify, opcode loop,
+ *                    loop cycles stalled on prefetched rows, on MT19937/applier
  */
 int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
                      size_t state_stride, const uint8_t* d_target_mem,
