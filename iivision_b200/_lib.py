@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libiivision_b200.so")
+LIB_PATH = os.environ.get("IIV_LIB_PATH") or os.path.join(_HERE, "libiivision_b200.so")
 
 MODE_HGR, MODE_DHGR = 0, 1
 LAYOUT_TRIANGULAR, LAYOUT_SYMMETRIC = 0, 1

@@ -37,6 +37,7 @@ struct Dests {
   uint16_t* p[kMaxDests];
   int n;
   int multicast;  // p[0] is an NVSwitch multicast mapping: one multimem.st reaches all
+  uint32_t one;   // the constant 1, opaque to the compiler (see tree_step_x2)
 };
 
 // 16-byte store through a multicast (multimem) address: the switch replicates it
@@ -182,93 +183,128 @@ chain_kernel(Lut lut, Dests dests, uint32_t row_begin, int triangular) {
 // the block stages in shared memory; a warp's 32 j-tiles make each row store
 // 512 contiguous bytes.  A step is: LDS.U8 of S[a][b] (a is warp-uniform, so the
 // 16-byte row is one broadcast wavefront), add, compare of the swap keys, min.
+#ifndef IIV_TREE_MIN_BLOCKS
+#define IIV_TREE_MIN_BLOCKS 5
+#endif
 constexpr int kTreeThreads = 128;
 constexpr int kTilesPerChunk = 16;   // i-tiles (of 8 rows) per block
 
+// Word offsets inside one i-tile descriptor in shared memory.  Scalar steps use
+// {address of S2[a_t][0], swap key}; the two innermost pixels are walked for two
+// rows at once in 16-bit halves and use {address of SP[a_t(row), a_t(row')][0],
+// swap keys of both rows}.
 template <int MODE>
 struct Tree {
-  static constexpr int kLeaf = MODE == IIV_MODE_HGR ? 4 : 3;
+  static constexpr bool kHgr = MODE == IIV_MODE_HGR;
+  static constexpr int kLeaf = kHgr ? 4 : 3;
   static constexpr int kSfx = Mode<MODE>::kDots - kLeaf;      // shared pixels
   static constexpr int kSfxPad = (kSfx + 1) & ~1;
-  // words of decoded i-side strings per tile: {lut row address, swap key} per pixel
-  static constexpr int kTileWords = 2 * kSfxPad + 8 * 2 * 4;
+  static constexpr int kMidOff = 2 * kSfxPad;   // HGR (mi, pixel 2|3); DHGR (i2, pixel 2)
+  static constexpr int kMidWords = kHgr ? 8 : 4;
+  static constexpr int kP1Off = kMidOff + kMidWords;   // pixel 1, row pairs
+  static constexpr int kP1Pairs = kHgr ? 4 : 2;
+  static constexpr int kP0Off = kP1Off + 2 * kP1Pairs;   // pixel 0, 4 row pairs
+  static constexpr int kTileWords = kP0Off + 8;
+  static constexpr int kItems = kSfx + kMidWords / 2 + kP1Pairs + 4;
 };
 
-constexpr uint32_t kInf = 0x3fffffffu;
-
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-
-// One chain step for the two innermost pixels (0 and 1), which carry 85 % of the
-// steps.  row = shared address of S[a_t][0] (16 bytes: a is warp-uniform, lanes
-// differ in b only, so the load is one conflict-free broadcast wavefront);
-// kf = a_t | a_{t+1} << 4; pb = b_t; kr = b_{t+1} | b_t << 4; f1 = F_{t+1};
-// h2 = F_{t+2} + 1.
-__device__ __forceinline__ uint32_t tree_step(uint32_t f1, uint32_t h2, uint32_t row,
-                                              uint32_t kf, uint32_t pb, uint32_t kr) {
-  uint32_t c = f1 + lds_u8(row + pb);
+// One chain step (scalar).  s = S2[a_t][kr] where S2[a][k] = S[a][k >> 4]; kf = a_t |
+// a_{t+1} << 4; kr = b_{t+1} | b_t << 4 serves as swap key AND table index; f1 =
+// F_{t+1}; h2 = F_{t+2} + 1.
+__device__ __forceinline__ uint32_t tree_step(uint32_t f1, uint32_t h2, uint32_t s,
+                                              uint32_t kf, uint32_t kr) {
+  uint32_t c = f1 + s;
   if (kf == kr) c = min(c, h2);
   return c;
 }
 
-// The same step for the outer pixels, where registers matter more than bank
-// conflicts: one per-lane register kr serves as swap key AND as index into the
-// widened table S2[a][kr] = S[a][kr >> 4] (row2 = shared address of S2[a_t][0]).
-__device__ __forceinline__ uint32_t tree_step2(uint32_t f1, uint32_t h2, uint32_t row2,
-                                               uint32_t kf, uint32_t kr) {
-  uint32_t c = f1 + lds_u8(row2 + kr);
-  if (kf == kr) c = min(c, h2);
-  return c;
+// The same step for two rows at once, values in 16-bit halves (all < 0x8000).
+// s2 = SP[a_t, a_t'][b_t], SP[a, a'][b] = S[a][b] | S[a'][b] << 16 (a, a' are
+// warp-uniform and lanes differ in b only: one conflict-free broadcast wavefront);
+// kf2 / kr2 = swap keys of both rows / of b in both halves.  A half whose keys differ
+// gets bit 15 set in the swap alternative, which the unsigned min then never takes:
+// VIADDMNMX.U16x2 does add + min for both rows.
+//
+// `one` is the constant 1 in a register the compiler cannot see through: the adds
+// written as x * one + y become IMAD on the FMA pipe, which otherwise idles while the
+// ALU pipe (LOP3 / VIADDMNMX / PRMT, half rate) is the bottleneck.
+__device__ __forceinline__ uint32_t tree_step_x2(uint32_t f1, uint32_t h2, uint32_t s2,
+                                                 uint32_t kf2, uint32_t kr2, uint32_t one) {
+  const uint32_t x = kf2 ^ kr2;
+  const uint32_t alt = ((x * one + 0x7fff7fffu) & 0x80008000u) | h2;
+  return __viaddmin_u16x2(f1, s2, alt);
 }
 
 template <int MODE, bool TRI, bool MULTI>
-__global__ void __launch_bounds__(kTreeThreads, 4)
+__global__ void __launch_bounds__(kTreeThreads, IIV_TREE_MIN_BLOCKS)
 tree_kernel(const __grid_constant__ Lut lut, const __grid_constant__ Dests dests,
             uint32_t row_begin, uint32_t row_end) {
   using M = Mode<MODE>;
   using T = Tree<MODE>;
   constexpr int n = M::kDots, L = T::kLeaf;
-  __shared__ __align__(16) uint8_t S[256];
   __shared__ __align__(16) uint8_t S2[16 * 256];
+  __shared__ __align__(16) uint32_t SP[256 * 16];
   __shared__ __align__(16) uint32_t idesc[kTilesPerChunk][T::kTileWords];
 
   const int tid = threadIdx.x;
   const int o = blockIdx.z;
-  for (int k = tid; k < 256; k += kTreeThreads) S[k] = lut.s[k];
-  for (int k = tid; k < 16 * 256; k += kTreeThreads)
+  for (int k = tid; k < 16 * 256; k += kTreeThreads) {
     S2[k] = lut.s[(k >> 8) * 16 + ((k & 255) >> 4)];
-  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(S);
-  const uint32_t s2_base = (uint32_t)__cvta_generic_to_shared(S2);
+    // k = (a << 4 | a') << 4 | b
+    SP[k] = (uint32_t)lut.s[(k >> 8) * 16 + (k & 15)] |
+            ((uint32_t)lut.s[((k >> 4) & 15) * 16 + (k & 15)] << 16);
+  }
+  const uint32_t one = dests.one;
+  // descriptors hold byte offsets into S2 / SP; lanes add their own b-dependent part
+  const auto s2_at = [&](uint32_t off) -> uint32_t { return S2[off]; };
+  const auto sp_at = [&](uint32_t off) -> uint32_t {
+    return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(SP) + off);
+  };
 
   // ---- i side: decode the chunk's strings into shared memory -----------------------
   const uint32_t tile0 = (row_begin >> 3) + blockIdx.y * kTilesPerChunk;
   const uint32_t tile_end = (row_end + 7) >> 3;
-  constexpr int kItems = T::kSfx + 8 * L;            // (pixel) items per tile
-  for (int item = tid; item < kTilesPerChunk * kItems; item += kTreeThreads) {
-    const int tl = item / kItems, k = item - tl * kItems;
+  for (int item = tid; item < kTilesPerChunk * T::kItems; item += kTreeThreads) {
+    const int tl = item / T::kItems;
+    int k = item - tl * T::kItems;
     const uint32_t tile = tile0 + tl;
     if (tile >= tile_end) continue;
-    int v, t, slot;
+    // scalar item: (value v, pixel t); paired item: (v, v2, t)
+    int v, v2 = -1, t, slot;
     if (k < T::kSfx) {
       v = 0; t = L + k; slot = 2 * k;
+    } else if ((k -= T::kSfx) < T::kMidWords / 2) {
+      if (T::kHgr) { v = 2 * (k >> 1); t = 2 + (k & 1); }   // (mi, pixel 2 | 3)
+      else { v = 4 * k; t = 2; }                              // (i2, pixel 2)
+      slot = T::kMidOff + 2 * k;
+    } else if ((k -= T::kMidWords / 2) < T::kP1Pairs) {
+      if (T::kHgr) { v = 2 * k; v2 = 2 * k + 1; }            // rows 2q, 2q+1
+      else { v = 4 * k; v2 = 4 * k + 2; }                     // i12 = 2q, 2q+1
+      t = 1; slot = T::kP1Off + 2 * k;
     } else {
-      v = (k - T::kSfx) / L; t = (k - T::kSfx) - v * L; slot = 2 * T::kSfxPad + 8 * v + 2 * t;
+      k -= T::kP1Pairs;
+      v = 2 * k; v2 = 2 * k + 1; t = 0; slot = T::kP0Off + 2 * k;
     }
     uint64_t lo; uint32_t hi;
     load_pixels<MODE>(o, tile * 8 + v, lo, hi);
     const uint32_t a = pixel_at(lo, hi, t);
-    const uint32_t a1 = t + 1 < n ? pixel_at(lo, hi, t + 1) : 0xffffu;
-    idesc[tl][slot] = t < 2 ? s_base + a * 16 : s2_base + a * 256;
-    idesc[tl][slot + 1] = a | (a1 << 4);
+    const uint32_t kf = a | ((t + 1 < n ? pixel_at(lo, hi, t + 1) : 0xffu) << 4);
+    if (v2 < 0) {
+      idesc[tl][slot] = a * 256;
+      idesc[tl][slot + 1] = kf;
+    } else {
+      load_pixels<MODE>(o, tile * 8 + v2, lo, hi);
+      const uint32_t a2 = pixel_at(lo, hi, t);
+      const uint32_t kf2 = a2 | (pixel_at(lo, hi, t + 1) << 4);
+      idesc[tl][slot] = (a << 4 | a2) << 6;
+      idesc[tl][slot + 1] = kf | (kf2 << 16);
+    }
   }
 
   // ---- j side: this thread's 8 strings, decoded into registers ----------------------
   const uint32_t jb = (blockIdx.x * kTreeThreads + tid) * 8;
   uint32_t sfx_kr[T::kSfx];
-  uint32_t leaf_pb[8][2], leaf_kr[8][L];
+  uint32_t leaf_pb4[8][2], leaf_kr2[8][2], mid_kr[8][L];
   {
     uint64_t lo; uint32_t hi;
 #pragma unroll
@@ -276,8 +312,12 @@ tree_kernel(const __grid_constant__ Lut lut, const __grid_constant__ Dests dests
       load_pixels<MODE>(o, jb + v, lo, hi);
 #pragma unroll
       for (int t = 0; t < L; ++t) {
-        if (t < 2) leaf_pb[v][t] = pixel_at(lo, hi, t);
-        leaf_kr[v][t] = pixel_at(lo, hi, t + 1) | (pixel_at(lo, hi, t) << 4);
+        const uint32_t kr = pixel_at(lo, hi, t + 1) | (pixel_at(lo, hi, t) << 4);
+        if (t < 2) {
+          leaf_pb4[v][t] = pixel_at(lo, hi, t) * 4;
+          leaf_kr2[v][t] = kr * 0x10001u;
+        }
+        mid_kr[v][t] = kr;
       }
       if (v == 0) {
 #pragma unroll
@@ -299,11 +339,9 @@ tree_kernel(const __grid_constant__ Lut lut, const __grid_constant__ Dests dests
 
     // One finished row of the tile: mask (reference file layout keeps j < i only;
     // tiles are 8-aligned on both axes) and store 16 bytes per destination.
-    auto emit = [&](int iv, const uint32_t (&r)[8]) {
+    auto emit = [&](int iv, uint4 v) {
       const uint32_t i = ib + iv;
       if (i < row_begin || i >= row_end) return;
-      uint4 v = make_uint4(r[0] | (r[1] << 16), r[2] | (r[3] << 16), r[4] | (r[5] << 16),
-                           r[6] | (r[7] << 16));
       if (TRI && jb >= ib) {
         if (jb > ib) {
           v = make_uint4(0, 0, 0, 0);
@@ -326,12 +364,18 @@ tree_kernel(const __grid_constant__ Lut lut, const __grid_constant__ Dests dests
         *reinterpret_cast<uint4*>(dests.p[0] + at) = v;
       }
     };
+    // r[jv] holds rows (iv, iv + 1) in its halves: un-zip into the two rows
+    auto emit_pair = [&](int iv, const uint32_t (&r)[8]) {
+      emit(iv, make_uint4(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410),
+                          __byte_perm(r[4], r[5], 0x5410), __byte_perm(r[6], r[7], 0x5410)));
+      emit(iv + 1, make_uint4(__byte_perm(r[0], r[1], 0x7632), __byte_perm(r[2], r[3], 0x7632),
+                              __byte_perm(r[4], r[5], 0x7632), __byte_perm(r[6], r[7], 0x7632)));
+    };
 
     // triangular layout: the whole warp lies above the diagonal -> zeros only
     if (TRI && __all_sync(0xffffffffu, jb >= ib + 8)) {
-      const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int iv = 0; iv < 8; ++iv) emit(iv, z);
+      for (int iv = 0; iv < 8; ++iv) emit(iv, make_uint4(0, 0, 0, 0));
       continue;
     }
 
@@ -339,76 +383,88 @@ tree_kernel(const __grid_constant__ Lut lut, const __grid_constant__ Dests dests
     uint32_t f1, f2;    // F_{t+1}, F_{t+2}
     {
       const uint2 a = *reinterpret_cast<const uint2*>(d + 2 * (T::kSfx - 1));
-      f1 = lds_u8(a.x + sfx_kr[T::kSfx - 1]);   // last pixel: no swap partner
+      f1 = s2_at(a.x + sfx_kr[T::kSfx - 1]);   // last pixel: no swap partner
       f2 = 0;
     }
 #pragma unroll
     for (int k = T::kSfx - 2; k >= 0; --k) {
       const uint2 a = *reinterpret_cast<const uint2*>(d + 2 * k);
-      const uint32_t f = tree_step2(f1, f2 + 1, a.x, a.y, sfx_kr[k]);
+      const uint32_t f = tree_step(f1, f2 + 1, s2_at(a.x + sfx_kr[k]), a.y, sfx_kr[k]);
       f2 = f1;
       f1 = f;
     }
-    const uint32_t* leaf = d + 2 * T::kSfxPad;     // [variant][pixel]{row, kf}
-    if (MODE == IIV_MODE_HGR) {
-      // pixels 3, 2 depend on bit 1 only
-      uint32_t F2v[2][2], H3v[2][2], H2v[2][2];
+    if (T::kHgr) {
+      // pixels 3, 2 depend on bit 1 only: 4 scalar (mi, mj) combinations
+      uint32_t F2p[2][2], H3p[2][2], H2p[2][2];
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi) {
-        const uint4 a23 = *reinterpret_cast<const uint4*>(leaf + 8 * (2 * mi) + 4);
+        const uint4 a23 = *reinterpret_cast<const uint4*>(d + T::kMidOff + 4 * mi);
 #pragma unroll
         for (int mj = 0; mj < 2; ++mj) {
-          const uint32_t f3 = tree_step2(f1, f2 + 1, a23.z, a23.w, leaf_kr[2 * mj][3]);
-          F2v[mi][mj] = tree_step2(f3, f1 + 1, a23.x, a23.y, leaf_kr[2 * mj][2]);
-          H3v[mi][mj] = f3 + 1;
-          H2v[mi][mj] = F2v[mi][mj] + 1;
+          const uint32_t f3 = tree_step(f1, f2 + 1, s2_at(a23.z + mid_kr[2 * mj][3]), a23.w,
+                                        mid_kr[2 * mj][3]);
+          const uint32_t g2 = tree_step(f3, f1 + 1, s2_at(a23.x + mid_kr[2 * mj][2]), a23.y,
+                                        mid_kr[2 * mj][2]);
+          F2p[mi][mj] = g2 * 0x10001u;
+          H3p[mi][mj] = (f3 + 1) * 0x10001u;
+          H2p[mi][mj] = (g2 + 1) * 0x10001u;
         }
       }
+      // pixels 1, 0: rows (2q, 2q+1) together, both have bit 1 = q & 1
 #pragma unroll
-      for (int iv = 0; iv < 8; ++iv) {
-        const int mi = (iv >> 1) & 1;
-        const uint4 a01 = *reinterpret_cast<const uint4*>(leaf + 8 * iv);
+      for (int q = 0; q < 4; ++q) {
+        const int mi = q & 1;
+        const uint2 a1 = *reinterpret_cast<const uint2*>(d + T::kP1Off + 2 * q);
+        const uint2 a0 = *reinterpret_cast<const uint2*>(d + T::kP0Off + 2 * q);
         uint32_t r[8];
 #pragma unroll
         for (int jv = 0; jv < 8; ++jv) {
           const int mj = (jv >> 1) & 1;
-          const uint32_t g1 = tree_step(F2v[mi][mj], H3v[mi][mj], a01.z, a01.w,
-                                        leaf_pb[jv][1], leaf_kr[jv][1]);
-          r[jv] = tree_step(g1, H2v[mi][mj], a01.x, a01.y, leaf_pb[jv][0], leaf_kr[jv][0]);
+          const uint32_t g1 = tree_step_x2(F2p[mi][mj], H3p[mi][mj],
+                                           sp_at(leaf_pb4[jv][1] * one + a1.x), a1.y,
+                                           leaf_kr2[jv][1], one);
+          r[jv] = tree_step_x2(g1, H2p[mi][mj], sp_at(leaf_pb4[jv][0] * one + a0.x), a0.y,
+                               leaf_kr2[jv][0], one);
         }
-        emit(iv, r);
+        emit_pair(2 * q, r);
       }
     } else {
       // pixel 2 <- bit 2; pixel 1 <- bits 1,2; pixel 0 <- bits 0,1,2
-      uint32_t F2v[2][2], H2v[2][2];
+      uint32_t F2p[2][2], H2p[2][2];
 #pragma unroll
       for (int i2 = 0; i2 < 2; ++i2) {
-        const uint2 a2 = *reinterpret_cast<const uint2*>(leaf + 8 * (4 * i2) + 4);
+        const uint2 a2 = *reinterpret_cast<const uint2*>(d + T::kMidOff + 2 * i2);
 #pragma unroll
         for (int j2 = 0; j2 < 2; ++j2) {
-          F2v[i2][j2] = tree_step2(f1, f2 + 1, a2.x, a2.y, leaf_kr[4 * j2][2]);
-          H2v[i2][j2] = F2v[i2][j2] + 1;
+          const uint32_t g2 = tree_step(f1, f2 + 1, s2_at(a2.x + mid_kr[4 * j2][2]), a2.y,
+                                        mid_kr[4 * j2][2]);
+          F2p[i2][j2] = g2 * 0x10001u;
+          H2p[i2][j2] = (g2 + 1) * 0x10001u;
         }
       }
-      const uint32_t h3 = f1 + 1;
+      const uint32_t h3p = (f1 + 1) * 0x10001u;
 #pragma unroll
-      for (int i12 = 0; i12 < 4; ++i12) {
-        const uint2 a1 = *reinterpret_cast<const uint2*>(leaf + 8 * (2 * i12) + 2);
-        uint32_t F1v[4];
+      for (int q1 = 0; q1 < 2; ++q1) {
+        // pixel 1 for i12 = 2 q1 and 2 q1 + 1 (both have bit 2 = q1)
+        const uint2 a1 = *reinterpret_cast<const uint2*>(d + T::kP1Off + 2 * q1);
+        uint32_t F1x[4];
 #pragma unroll
         for (int j12 = 0; j12 < 4; ++j12)
-          F1v[j12] = tree_step(F2v[i12 >> 1][j12 >> 1], h3, a1.x, a1.y,
-                               leaf_pb[2 * j12][1], leaf_kr[2 * j12][1]);
+          F1x[j12] = tree_step_x2(F2p[q1][j12 >> 1], h3p,
+                                  sp_at(leaf_pb4[2 * j12][1] * one + a1.x), a1.y,
+                                  leaf_kr2[2 * j12][1], one);
 #pragma unroll
-        for (int i0 = 0; i0 < 2; ++i0) {
-          const int iv = 2 * i12 + i0;
-          const uint2 a0 = *reinterpret_cast<const uint2*>(leaf + 8 * iv);
+        for (int half = 0; half < 2; ++half) {
+          const int q0 = 2 * q1 + half;           // rows 2 q0, 2 q0 + 1: i12 = q0
+          const uint2 a0 = *reinterpret_cast<const uint2*>(d + T::kP0Off + 2 * q0);
           uint32_t r[8];
 #pragma unroll
-          for (int jv = 0; jv < 8; ++jv)
-            r[jv] = tree_step(F1v[jv >> 1], H2v[i12 >> 1][jv >> 2], a0.x, a0.y,
-                              leaf_pb[jv][0], leaf_kr[jv][0]);
-          emit(iv, r);
+          for (int jv = 0; jv < 8; ++jv) {
+            const uint32_t parent = __byte_perm(F1x[jv >> 1], 0, half ? 0x3232 : 0x1010);
+            r[jv] = tree_step_x2(parent, H2p[q1][jv >> 2], sp_at(leaf_pb4[jv][0] * one + a0.x),
+                                 a0.y, leaf_kr2[jv][0], one);
+          }
+          emit_pair(2 * q0, r);
         }
       }
     }
@@ -569,6 +625,7 @@ extern "C" int iiv_table_generate(int mode, const int32_t* h_lut,
   IIV_REQUIRE(h_lut && d_table, "null pointer");
   Dests dests = {};
   dests.n = 1;
+  dests.one = 1;
   dests.p[0] = d_table;
   return generate_any(mode, h_lut, dests, row_begin, row_end, layout, algo, stream);
 }
@@ -583,6 +640,7 @@ extern "C" int iiv_table_generate_scatter(int mode, const int32_t* h_lut,
   IIV_REQUIRE(n_ranks >= 1 && n_ranks <= kMaxDests && rank >= 0 && rank < n_ranks,
               "bad rank %d of %d", rank, n_ranks);
   Dests dests = {};
+  dests.one = 1;
   if (d_multicast_table) {
     dests.n = 1;
     dests.multicast = 1;
