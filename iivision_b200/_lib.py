@@ -41,6 +41,9 @@ PROTOTYPES = {
                                    c_void_p]),
     "iiv_masked_update": (c_int, [c_int, c_int, c_void_p, c_u8, c_void_p,
                                   c_size_t, c_void_p]),
+    "iiv_column_part": (c_int, [c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "iiv_fix_column": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                               c_void_p]),
     "iiv_fix_array_neighbours": (c_int, [c_int, c_int, c_void_p, c_int,
                                          c_void_p]),
     "iiv_diff_weights": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int,

@@ -56,6 +56,34 @@ __global__ void masked_update_kernel(int o, const uint64_t* __restrict__ in,
   if (k < n) out[k] = masked_update<MODE>(o, in[k], v);
 }
 
+template <int MODE>
+__global__ void column_part_kernel(int part, const uint64_t* __restrict__ in,
+                                   uint64_t* __restrict__ out, size_t n) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint64_t w = in[k];
+  uint64_t r;
+  if (part == IIV_PART_HEADER)
+    r = header_of<MODE>(w);
+  else if (part == IIV_PART_FOOTER)
+    r = footer_of<MODE>(w);
+  else if (part == IIV_PART_BODY)
+    r = w & keep_low_mask<MODE>() & keep_high_mask<MODE>();
+  else
+    r = double_pixels((uint32_t)w & 0x7fu);
+  out[k] = r;
+}
+
+template <int MODE>
+__global__ void fix_column_kernel(int side, const uint64_t* __restrict__ neighbour,
+                                  const uint64_t* __restrict__ column,
+                                  uint64_t* __restrict__ out, size_t n) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  out[k] = side == 0 ? (neighbour[k] & keep_low_mask<MODE>()) ^ footer_of<MODE>(column[k])
+                     : (neighbour[k] & keep_high_mask<MODE>()) ^ header_of<MODE>(column[k]);
+}
+
 // Bitmap._fix_array_neighbours (screen.py:322-341): np.roll wraps inside a row.
 template <int MODE>
 __global__ void __launch_bounds__(128)
@@ -245,6 +273,32 @@ extern "C" int iiv_masked_update(int mode, int byte_offset, const uint64_t* d_ol
   cudaStream_t st = (cudaStream_t)stream;
   IIV_DISPATCH(mode, masked_update_kernel, (unsigned)((n + 255) / 256), 256, st,
                byte_offset, d_old, (uint32_t)value, d_new, n);
+  return 0;
+}
+
+extern "C" int iiv_column_part(int mode, int part, const uint64_t* d_in, uint64_t* d_out,
+                               size_t n, void* stream) {
+  IIV_REQUIRE(mode_ok(mode), "bad mode %d", mode);
+  IIV_REQUIRE(part >= IIV_PART_HEADER && part <= IIV_PART_DOUBLE, "bad part %d", part);
+  IIV_REQUIRE(!(part == IIV_PART_DOUBLE && mode != IIV_MODE_HGR), "_double_pixels is HGR only");
+  IIV_REQUIRE(d_in && d_out, "null pointer");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  IIV_DISPATCH(mode, column_part_kernel, (unsigned)((n + 255) / 256), 256, st, part, d_in,
+               d_out, n);
+  return 0;
+}
+
+extern "C" int iiv_fix_column(int mode, int side, const uint64_t* d_neighbour,
+                              const uint64_t* d_column, uint64_t* d_out, size_t n,
+                              void* stream) {
+  IIV_REQUIRE(mode_ok(mode), "bad mode %d", mode);
+  IIV_REQUIRE(side == 0 || side == 1, "bad side %d", side);
+  IIV_REQUIRE(d_neighbour && d_column && d_out, "null pointer");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  IIV_DISPATCH(mode, fix_column_kernel, (unsigned)((n + 255) / 256), 256, st, side,
+               d_neighbour, d_column, d_out, n);
   return 0;
 }
 

@@ -221,6 +221,28 @@ def masked_update(mode, byte_offset, old: torch.Tensor, value: int) -> torch.Ten
     return out
 
 
+PART_HEADER, PART_FOOTER, PART_BODY, PART_DOUBLE = 0, 1, 2, 3
+
+
+def column_part(mode, part: int, words: torch.Tensor) -> torch.Tensor:
+    """_make_header / _make_footer / body bits / _double_pixels, elementwise."""
+    m = mode_id(mode)
+    out = torch.empty_like(words)
+    check(lib.iiv_column_part(m, part, _ptr(words), _ptr(out), words.numel(), _stream()))
+    return out
+
+
+def fix_column(mode, side: int, neighbour: torch.Tensor, column: torch.Tensor) -> torch.Tensor:
+    """_fix_column_left (side 0) / _fix_column_right (side 1), elementwise."""
+    m = mode_id(mode)
+    if neighbour.shape != column.shape:
+        raise ValueError("neighbour and column must have the same shape")
+    out = torch.empty_like(neighbour)
+    check(lib.iiv_fix_column(m, side, _ptr(neighbour), _ptr(column), _ptr(out),
+                             neighbour.numel(), _stream()))
+    return out
+
+
 def fix_array_neighbours(mode, byte_offset, rows: torch.Tensor) -> torch.Tensor:
     m = mode_id(mode)
     if rows.shape[-1] != 128:

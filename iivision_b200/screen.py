@@ -165,6 +165,49 @@ class Bitmap:
         self._pack()
 
     # -- packing -----------------------------------------------------------------
+    @classmethod
+    def _part(cls, part: int, col: IntOrArray) -> IntOrArray:
+        if cls.MODE is None:
+            raise NotImplementedError
+        scalar = np.ndim(col) == 0
+        arr = np.atleast_1d(np.asarray(col, dtype=np.uint64))
+        out = _d2h_u64(ops.column_part(cls.MODE, part, _h2d_u64(arr))).reshape(arr.shape)
+        return np.uint64(out[0]) if scalar else out
+
+    @classmethod
+    def _make_header(cls, col: IntOrArray) -> IntOrArray:
+        """Extract values to use as header of next column."""
+        return cls._part(ops.PART_HEADER, col)
+
+    @classmethod
+    def _make_footer(cls, col: IntOrArray) -> IntOrArray:
+        """Extract values to use as footer of previous column."""
+        return cls._part(ops.PART_FOOTER, col)
+
+    def _body(self) -> np.ndarray:
+        """Pack related screen bytes into an efficient representation (no header /
+        footer bits)."""
+        main = _h2d_u8(self.main_memory.page_offset)
+        aux = _h2d_u8(self.aux_memory.page_offset) if self.aux_memory is not None \
+            and self.MODE == ops.MODE_DHGR else None
+        return _d2h_u64(ops.column_part(self.MODE, ops.PART_BODY,
+                                        ops.pack(self.MODE, main, aux)))
+
+    def _fix_column_left(self, column_left: IntOrArray, column: IntOrArray) -> IntOrArray:
+        """Patch up the footer of the column to the left."""
+        return self._fix_column(0, column_left, column)
+
+    def _fix_column_right(self, column_right: IntOrArray, column: IntOrArray) -> IntOrArray:
+        """Patch up the header of the column to the right."""
+        return self._fix_column(1, column_right, column)
+
+    def _fix_column(self, side, neighbour, column):
+        scalar = np.ndim(neighbour) == 0
+        a = np.atleast_1d(np.asarray(neighbour, dtype=np.uint64))
+        b = np.broadcast_to(np.asarray(column, dtype=np.uint64), a.shape)
+        out = _d2h_u64(ops.fix_column(self.MODE, side, _h2d_u64(a), _h2d_u64(b))).reshape(a.shape)
+        return np.uint64(out[0]) if scalar else out
+
     def _pack(self) -> None:
         """Pack MemoryMap into efficient representation for diffing
         (screen.py:207-226 -> iiv_pack)."""
@@ -335,6 +378,11 @@ class HGRBitmap(Bitmap):
 
     def __init__(self, palette: pal.Palette, main_memory: MemoryMap):
         super(HGRBitmap, self).__init__(palette, main_memory, None)
+
+    @classmethod
+    def _double_pixels(cls, int7: int) -> int:
+        """Each bit 0..5 becomes two dots, bit 6 three (screen.py:710-739)."""
+        return int(cls._part(ops.PART_DOUBLE, np.uint64(int7)))
 
     @staticmethod
     @functools.lru_cache(None)

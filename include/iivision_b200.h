@@ -122,6 +122,25 @@ int iiv_mask_and_shift(int mode, int byte_offset, const uint64_t* d_in,
 int iiv_masked_update(int mode, int byte_offset, const uint64_t* d_old,
                       uint8_t value, uint64_t* d_new, size_t n, void* stream);
 
+/* Static helpers of the bitmap classes, elementwise over n words:
+ *   IIV_PART_HEADER  Bitmap._make_header (screen.py:650-661 HGR, :921-924 DHGR)
+ *   IIV_PART_FOOTER  Bitmap._make_footer (screen.py:679-690 HGR, :949-952 DHGR)
+ *   IIV_PART_BODY    a packed word with header and footer bits cleared (what
+ *                    Bitmap._body returns, screen.py:663-677, :926-947)
+ *   IIV_PART_DOUBLE  HGRBitmap._double_pixels (screen.py:710-739), HGR only */
+#define IIV_PART_HEADER 0
+#define IIV_PART_FOOTER 1
+#define IIV_PART_BODY 2
+#define IIV_PART_DOUBLE 3
+int iiv_column_part(int mode, int part, const uint64_t* d_in, uint64_t* d_out,
+                    size_t n, void* stream);
+
+/* Bitmap._fix_column_left (side 0, screen.py:295-306): footer of d_neighbour :=
+ * first bits of d_column; _fix_column_right (side 1, :308-320): header of
+ * d_neighbour := last bits of d_column.  Elementwise over n words. */
+int iiv_fix_column(int mode, int side, const uint64_t* d_neighbour,
+                   const uint64_t* d_column, uint64_t* d_out, size_t n, void* stream);
+
 /* Bitmap._fix_array_neighbours (screen.py:322-341) on rows of 128 words. */
 int iiv_fix_array_neighbours(int mode, int byte_offset, uint64_t* d_rows,
                              int n_rows, void* stream);

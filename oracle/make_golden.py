@@ -17,6 +17,8 @@ The reference cannot travel to the GPU box, so its outputs do, as fixtures:
                        Video.encode_frame (video.py:72-301) under the Movie.encode
                        schedule, with random.seed(s); np.random.seed(s), plus the
                        encoder state and the next words of both RNG streams
+  helpers.npz          _make_header, _make_footer, _body, _fix_column_left/right and
+                       _double_pixels outputs of the reference classes
   luts.json            int(dE2000) substitution matrices from oracle/cie2000.py
                        (restated colormath; NOT reference output -- the reference
                        generator cannot run offline) together with the rows
@@ -152,6 +154,31 @@ def gen_scorer(ns, mode, table):
     np.savez_compressed(os.path.join(GOLDEN, "scorer_%s.npz" % mode.lower()), **out)
 
 
+def gen_helpers(ns):
+    """Static helpers of the bitmap classes on seeded words (screen.py:650-739,
+    :921-952, :295-320)."""
+    out = {}
+    rng = np.random.default_rng(31)
+    for mode, cls in (("HGR", ns.screen.HGRBitmap), ("DHGR", ns.screen.DHGRBitmap)):
+        width = int(cls.HEADER_BITS + cls.BODY_BITS + cls.FOOTER_BITS)
+        words = rng.integers(0, 1 << width, size=(6, 128), dtype=np.uint64)
+        other = rng.integers(0, 1 << width, size=(6, 128), dtype=np.uint64)
+        bm = ref_bitmap(ns, mode, np.zeros((32, 256), np.uint8), np.zeros((32, 256), np.uint8))
+        out[mode + "_words"] = words
+        out[mode + "_other"] = other
+        out[mode + "_header"] = cls._make_header(words.copy())
+        out[mode + "_footer"] = cls._make_footer(words.copy())
+        out[mode + "_fix_left"] = bm._fix_column_left(other.copy(), words.copy())
+        out[mode + "_fix_right"] = bm._fix_column_right(other.copy(), words.copy())
+        fr = synth.synthetic_frames(mode, 1, 1.0, seed=33)
+        b2 = ref_bitmap(ns, mode, fr[0, 0].copy(), fr[0, 1].copy() if mode == "DHGR" else None)
+        out[mode + "_frame"] = fr[0]
+        out[mode + "_body"] = b2._body().astype(np.uint64)
+    out["double_pixels"] = np.array(
+        [ns.screen.HGRBitmap._double_pixels(v) for v in range(128)], np.uint64)
+    np.savez_compressed(os.path.join(GOLDEN, "helpers.npz"), **out)
+
+
 def gen_stream(ns, case, table):
     name, mode, n_frames, fraction, fseed, seed, per_frame, flip = case
     ref_harness.install_tables(ns, mode, {5: table})
@@ -216,6 +243,9 @@ def gen_luts():
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ns = ref_harness.load()
+    print("helpers"); gen_helpers(ns)
+    if "--helpers-only" in sys.argv:
+        return
     print("pixel strings"); gen_pixel_strings(ns)
     print("luts"); gen_luts()
     for mode in ("HGR", "DHGR"):

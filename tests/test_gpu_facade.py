@@ -199,3 +199,28 @@ def test_video_sync_mid_generator(mods, oracle_tables):
     assert np.array_equal(v.memory_map.page_offset, ov.main)
     assert np.array_equal(v.update_priority, ov.update_priority)
     assert v.tick(0) and not v.tick(1) and v.tick(490)
+
+
+def test_static_helpers_against_reference_fixture(mods):
+    """_make_header / _make_footer / _body / _fix_column_* / _double_pixels against
+    outputs of the reference classes (tests/golden/helpers.npz)."""
+    g = np.load(os.path.join(GOLDEN, "helpers.npz"))
+    s = mods.screen
+    for mode, cls in (("HGR", s.HGRBitmap), ("DHGR", s.DHGRBitmap)):
+        words, other = g[mode + "_words"], g[mode + "_other"]
+        assert np.array_equal(cls._make_header(words), g[mode + "_header"])
+        assert np.array_equal(cls._make_footer(words), g[mode + "_footer"])
+        assert cls._make_header(words[0, 0]) == g[mode + "_header"][0, 0]
+        fr = g[mode + "_frame"]
+        mm = s.MemoryMap(1, fr[0].copy())
+        bm = (s.DHGRBitmap(mods.palette.Palette.NTSC, mm, s.MemoryMap(1, fr[1].copy()))
+              if mode == "DHGR" else s.HGRBitmap(mods.palette.Palette.NTSC, mm))
+        assert np.array_equal(bm._body(), g[mode + "_body"])
+        assert np.array_equal(bm._fix_column_left(other, words), g[mode + "_fix_left"])
+        assert np.array_equal(bm._fix_column_right(other, words), g[mode + "_fix_right"])
+    got = [s.HGRBitmap._double_pixels(v) for v in range(128)]
+    assert got == g["double_pixels"].tolist()
+    # literal from the reference's own unit test (screen_test.py:489-497)
+    assert s.HGRBitmap._double_pixels(0b1010101) == 0b111001100110011
+    with pytest.raises(Exception):
+        s.DHGRBitmap._part(3, np.uint64(1))
