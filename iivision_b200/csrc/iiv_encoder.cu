@@ -34,7 +34,9 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kProducers = kWarps - 3;  // warp 0 consumes, 1..5 produce, 6 applies, 7 twists
+constexpr int kProducers = 3;            // row-scoring warps (each keeps two rows in flight)
+constexpr int kFronts = 2;               // front-end warps of the opcode loop
+constexpr int kRecRing = 8;              // popped entries digested ahead of the decision warp
 constexpr int kOpQueue = 64;            // emitted opcodes waiting for their stores
 constexpr int kRing = 16;               // prefetched delta rows in flight
 constexpr int kCells = 32 * 256;       // one bank: 32 pages x 256 offsets
@@ -79,6 +81,14 @@ struct Smem {
   // emitted records waiting for warp 6 to apply their stores; byte 7 of a record
   // carries (sequence number & 255), so one 64-bit store publishes it
   unsigned long long opq[kOpQueue];
+  // front-end records: a popped heap entry with its candidate analysis (see phase B)
+  alignas(16) uint16_t rec_khi[kRecRing][256];   // per offset: (delta + 32768) & 0xffff
+  uint32_t rec_lane[kRecRing][32];               // per lane: cand bits | elig bits << 8 | rank << 16
+  uint32_t rec_hdr[kRecRing][4];                 // entry, cell | content << 16, n_cand, b_done seen
+  uint32_t rec_tag[kRecRing];                    // record number the slot holds
+  volatile int pop_turn;          // next record number to be popped
+  volatile int pop_cursor;        // sorted-heap cursor of that pop
+  volatile int b_done;            // records the decision warp has finished with
   volatile int final_emitted;     // total records of the segment (set before stop)
   volatile int applied_pub;       // records applied so far
   volatile int head;              // heap entries the consumer is done with
@@ -109,6 +119,17 @@ __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
   for (int t = lane; t < 169; t += 32) d[454 + t] = mt_mix(s[454 + t], s[455 + t], d[227 + t]);
   if (lane == 0) d[623] = mt_mix(s[623], d[0], d[396]);
   __syncwarp();
+}
+
+// 16-byte shared-memory load that the compiler neither caches nor moves (data that
+// another warp publishes behind a flag).
+__device__ __forceinline__ uint4 lds_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"((uint32_t)__cvta_generic_to_shared(p))
+               : "memory");
+  return v;
 }
 
 // getrandbits(8) bytes of one block of stream P into its slot(s) of py_nonce.
@@ -454,24 +475,37 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     const int n_first = n_sorted;   // entries of the sorted array phase B may walk
 
     // ======================= phase B: emit opcodes ==============================
-    // Warp-specialised so that the sequential chain never waits on HBM and never
-    // crosses a block barrier:
-    //   warp 0      consumer: pops the heap, evaluates the 256 candidate offsets of
-    //               the page (8 per lane), draws nonces, picks the two best and
-    //               publishes the opcode -- shared memory and warp shuffles only;
-    //   warps 1..5  producers: run ahead along the sorted heap and score the row of
-    //               new diffs of each upcoming entry (two dependent global loads:
-    //               target word, table gather) into a ring in shared memory.  A row
-    //               depends on the target frame and the content byte only, never on
-    //               the evolving source, so it cannot go stale;
-    //   warp 6      applier: commits the stores of every published opcode to the
-    //               source bitmap and memory map (Bitmap.apply), in order.  Nothing
-    //               in phase B reads the source, so this is off the critical path;
-    //   warp 7      twists the next MT19937 block of stream P in the background.
-    // A cell whose priority is already 0 is skipped by producer and consumer alike
-    // (priorities only ever fall to 0 inside a segment, video.py:140, :159-170).
+    // The opcode loop is a chain -- each opcode's nonces start where the previous
+    // one's ended, and its stores change the priorities the next pop sees -- so it is
+    // cut into stages run by specialised warps, none of which crosses a block barrier:
+    //   producers (warps 0-2)  run ahead along the sorted heap and score the row of
+    //       new diffs of each upcoming entry (two dependent global loads: target word,
+    //       table gather) into a ring in shared memory, two entries in flight per warp.
+    //       A row depends on the target frame and the content byte only, never on the
+    //       evolving source, so it cannot go stale.
+    //   front ends (warps 5, 6)  take turns popping the next live heap entry and
+    //       digest it SPECULATIVELY against the current priorities / diff weights of
+    //       its page: candidate bits, eligibility bits, nonce ranks and key prefixes of
+    //       all 256 offsets go into a record ring.
+    //   decision (warp 7)  consumes the records in order.  A record is valid unless an
+    //       opcode decided after the front end read the page touched the same page
+    //       (only stores to that page change what was read); then the warp re-digests
+    //       the entry itself.  It draws the nonces, picks the two best offsets, updates
+    //       priorities, re-queues, publishes the opcode: shared memory + shuffles only.
+    //   applier (warp 4)  commits the stores of every published opcode to the source
+    //       bitmap and memory map (Bitmap.apply), in order.  Nothing in phase B reads
+    //       the source, so this is off the chain.
+    //   twister (warp 3)  prepares the next MT19937 block of stream P in the background.
+    // A cell whose priority is already 0 is skipped by everyone alike: priorities only
+    // ever fall to 0 inside a segment (video.py:140, :159-170).
+    // The issue arbiter favours the highest warp id of a scheduler and a spinning warp
+    // is nearly always eligible, hence the decision warp is 7 and shares its scheduler
+    // (warp id % 4) with the mostly idle twister; helper loops back off with nanosleep.
     constexpr uint32_t kFull = 0xffffffffu;
+    constexpr int kDecideWarp = 7, kTwistWarp = 3, kApplyWarp = 4;
+    constexpr uint32_t kEndOfHeap = 0xffffffffu, kDeadRecord = 0xffffffffu;
     if (t < kRing) sm.ring_tag[t] = 0xffffffffu;
+    if (t < kRecRing) sm.rec_tag[t] = 0xffffffffu;
     if (t == 0) {
       sm.head = 0;
       sm.stop = 0;
@@ -479,6 +513,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       sm.mt_done = 0;
       sm.final_emitted = 0;
       sm.applied_pub = 0;
+      sm.pop_turn = 0;
+      sm.pop_cursor = 0;
+      sm.b_done = 0;
     }
     if (t < kOpQueue) sm.opq[t] = 0ull;
     __syncthreads();
@@ -486,22 +523,76 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     int emitted = 0, py_words = 0;
     bool out_of_work = false;
     const long long clk_b = clock64();
-    long long wait_rows = 0, wait_misc = 0;   // consumer stall cycles (diagnostics)
+    long long wait_rows = 0, wait_misc = 0;   // decision-warp stall cycles (diagnostics)
+    volatile uint32_t* tags = sm.ring_tag;
+    volatile uint32_t* rtags = sm.rec_tag;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
-    // Warp roles.  The SM's issue arbiter favours the highest warp id of a scheduler
-    // and a spinning warp is nearly always eligible, so the consumer is the highest
-    // warp (7) and shares its scheduler (warp id % 4) with the mostly-idle MT warp
-    // (3); every waiting loop of the helper warps backs off with __nanosleep.
-    constexpr int kConsumerWarp = 7, kTwistWarp = 3, kApplyWarp = 6;
-    const int producer_idx = warp < 3 ? warp : warp - 1;   // warps 0,1,2,4,5 -> 0..4
-    if (warp == kConsumerWarp) {
-      int cursor = 0, n_pushed = 0, mt_issued = 0, mt_seen = 0;
-      volatile uint32_t* tags = sm.ring_tag;
-      const uint32_t lt_mask = (1u << lane) - 1u;
+    // Candidate analysis of the 8 offsets a lane owns on `page` for the entry at
+    // `cell` whose row of new diffs is `row`: candidate bits (delta < 0, video.py:283),
+    // eligibility bits (priority != 0, video.py:159), nonce rank of the lane's first
+    // candidate, key prefixes, and the page's candidate count.
+    auto digest = [&](int cell, const uint16_t* row, uint32_t (&khi)[8], uint32_t& m8,
+                      uint32_t& e8, int& rank, int& n_cand) {
+      const int page = cell >> 8, off = cell & 255;
+      const int base = page * 256 + 8 * lane;
+      const uint4 ndv = lds_v4(row + 8 * lane);
+      const uint4 dwv = lds_v4(&sm.dw[base]);
+      const uint4 pu0 = lds_v4(&sm.prio[base]);
+      const uint4 pu1 = lds_v4(&sm.prio[base + 4]);
+      const int4 pr0 = make_int4((int)pu0.x, (int)pu0.y, (int)pu0.z, (int)pu0.w);
+      const int4 pr1 = make_int4((int)pu1.x, (int)pu1.y, (int)pu1.z, (int)pu1.w);
+      const uint32_t nd[8] = {ndv.x & 0xffffu, ndv.x >> 16, ndv.y & 0xffffu, ndv.y >> 16,
+                              ndv.z & 0xffffu, ndv.z >> 16, ndv.w & 0xffffu, ndv.w >> 16};
+      const uint32_t dwl[8] = {dwv.x & 0xffffu, dwv.x >> 16, dwv.y & 0xffffu, dwv.y >> 16,
+                               dwv.z & 0xffffu, dwv.z >> 16, dwv.w & 0xffffu, dwv.w >> 16};
+      const int pr[8] = {pr0.x, pr0.y, pr0.z, pr0.w, pr1.x, pr1.y, pr1.z, pr1.w};
+      // the popped cell itself has its diff weight and priority zeroed first
+      // (video.py:140-141): never a candidate
+      const uint32_t not_mine = lane == (off >> 3) ? ~(1u << (off & 7)) : ~0u;
+      m8 = 0;
+      e8 = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int delta = (int)nd[j] - (int)dwl[j];
+        khi[j] = (uint32_t)(delta + 32768) & 0xffffu;
+        m8 |= (delta < 0 ? 1u : 0u) << j;
+        e8 |= (pr[j] != 0 ? 1u : 0u) << j;
+      }
+      m8 &= not_mine;
+      e8 &= not_mine;
+      rank = 0;
+      n_cand = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t bal = __ballot_sync(kFull, (m8 >> j) & 1u);
+        rank += __popc(bal & lt_mask);
+        n_cand += __popc(bal);
+      }
+    };
+    // First live entry of the sorted heap at or after `cursor` (32 entries per probe).
+    auto probe = [&](int cursor) -> int {
+      while (cursor < n_first) {
+        const int idx = cursor + lane;
+        bool live = false;
+        if (idx < n_first)
+          live = reinterpret_cast<volatile int32_t*>(sm.prio)[(int)(sm.keys[idx] & 0x1fffu)] != 0;
+        const uint32_t bal = __ballot_sync(kFull, live);   // video.py:130
+        if (bal) return cursor + __ffs(bal) - 1;
+        cursor += 32;
+      }
+      return -1;
+    };
+
+    if (warp == kDecideWarp) {
+      int n_pushed = 0, mt_issued = 0, mt_seen = 0;
+      int r = 0;                 // next front-end record
+      bool heap_done = false;    // sorted heap exhausted: re-queued cells only
+      uint32_t hist = 0xffu;     // lane l < 16: page of the record r' = l (mod 16) decided last
       while (emitted < budget) {
         // ---- stream P bookkeeping: two resident 624-word blocks ----------------------
-        // (every lane polls the same shared word in one broadcast load, so the
-        // loop conditions below are warp-uniform)
+        // (every lane polls the same shared word in one broadcast load, so the loop
+        // conditions below are warp-uniform)
         if (pos_py > 624) {
           while (mt_seen < mt_issued) mt_seen = sm.mt_done;
           py_cur ^= 1;
@@ -515,41 +606,62 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         }
         const uint8_t* nonces = sm.py_nonce + py_cur * 624 + pos_py;
 
-        // ---- pop: first live entry of the sorted heap, 32 entries per probe --------------
-        int e = -1;
-        while (cursor < n_first) {
-          const int idx = cursor + lane;
-          bool live = false;
-          if (idx < n_first) live = sm.prio[(int)(sm.keys[idx] & 0x1fffu)] != 0;   // video.py:130
-          const uint32_t bal = __ballot_sync(kFull, live);
-          if (bal) {
-            e = cursor + __ffs(bal) - 1;
-            cursor = e + 1;
-            break;
-          }
-          cursor += 32;
-        }
-        int cell, slot;
-        uint32_t content;
-        if (e >= 0) {
-          if (lane == 0) sm.head = e;
-          cell = (int)(sm.keys[e] & 0x1fffu);
-          slot = e % kRing;
-          uint32_t tag = tags[slot];
-          if ((tag >> 8) != (uint32_t)e) {
+        int cell, slot, rank, n_cand;
+        uint32_t content, m8, e8, khi[8];
+        bool have = false;
+        if (!heap_done) {
+          // ---- next record of the front ends -------------------------------------------
+          const int rs = r % kRecRing;
+          if (rtags[rs] != (uint32_t)r) {
             const long long c0 = clock64();
-            do {
-              tag = tags[slot];
-            } while ((tag >> 8) != (uint32_t)e);
+            while (rtags[rs] != (uint32_t)r) {}
             wait_rows += clock64() - c0;
           }
-          // shared-memory accesses of one warp are performed in program order: the
-          // row written before the tag is visible once the tag is
           asm volatile("" ::: "memory");
-          content = tag & 0xffu;      // video.py:134
-        } else {
+          const uint4 hdr = lds_v4(sm.rec_hdr[rs]);
+          if (hdr.x == kEndOfHeap) {
+            heap_done = true;
+            if (lane == 0) sm.head = n_first;
+          } else {
+            const int e = (int)hdr.x;
+            cell = (int)(hdr.y & 0xffffu);
+            content = hdr.y >> 16;
+            slot = e % kRing;
+            if (lane == 0) sm.head = e;
+            // valid unless a record decided after the front end's read hit this page
+            const int seen = (int)hdr.w;
+            const bool in_window = lane < 16 && ((r - 1 - lane) & 15) < r - seen;
+            const bool conflict =
+                __ballot_sync(kFull, in_window && hist == (uint32_t)(cell >> 8)) != 0;
+            if (hdr.w == kDeadRecord) {
+              // dropped by the front end: the cell is zero
+            } else if (!conflict) {
+              const uint4 kv = lds_v4(&sm.rec_khi[rs][8 * lane]);
+              const uint32_t li = reinterpret_cast<volatile uint32_t*>(sm.rec_lane[rs])[lane];
+              khi[0] = kv.x & 0xffffu; khi[1] = kv.x >> 16; khi[2] = kv.y & 0xffffu;
+              khi[3] = kv.y >> 16; khi[4] = kv.z & 0xffffu; khi[5] = kv.z >> 16;
+              khi[6] = kv.w & 0xffffu; khi[7] = kv.w >> 16;
+              m8 = li & 0xffu;
+              e8 = (li >> 8) & 0xffu;
+              rank = (int)(li >> 16);
+              n_cand = (int)hdr.z;
+              have = true;
+            } else if (sm.prio[cell] != 0) {
+              digest(cell, sm.ring_row[slot], khi, m8, e8, rank, n_cand);
+              have = true;
+            }
+            // else: the cell was zeroed meanwhile -- it would be popped and skipped
+            if (lane == ((r & 15))) hist = have ? (uint32_t)(cell >> 8) : 0xffu;
+            ++r;
+            if (!have) {
+              __syncwarp();
+              if (lane == 0) sm.b_done = r;
+              continue;
+            }
+          }
+        }
+        if (heap_done) {
           // first-pass heap exhausted: arg-min over live re-queued cells, scored on demand
-          if (lane == 0) sm.head = n_first;
           uint64_t best = kDead;
           for (int k = lane; k < n_pushed; k += 32) {
             const uint64_t key = sm.pushed[k];
@@ -573,41 +685,12 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           score_row<MODE>(tp + (cell >> 8) * 128, table, content, is_aux, lane,
                           sm.ring_row[kRing]);
           __syncwarp();
+          digest(cell, sm.ring_row[kRing], khi, m8, e8, rank, n_cand);
         }
         const int page = cell >> 8, off = cell & 255;
         if (MODE == IIV_MODE_DHGR && content >= 0x80u) error_flags |= 1;  // :137
 
-        // ---- _compute_error: 8 candidate offsets per lane, branch-free --------------------
-        const int base = page * 256 + 8 * lane;
-        const uint4 ndv = reinterpret_cast<const uint4*>(sm.ring_row[slot])[lane];
-        const uint4 dwv = *reinterpret_cast<const uint4*>(&sm.dw[base]);
-        const int4 pr0 = *reinterpret_cast<const int4*>(&sm.prio[base]);
-        const int4 pr1 = *reinterpret_cast<const int4*>(&sm.prio[base + 4]);
-        const uint32_t nd[8] = {ndv.x & 0xffffu, ndv.x >> 16, ndv.y & 0xffffu, ndv.y >> 16,
-                                ndv.z & 0xffffu, ndv.z >> 16, ndv.w & 0xffffu, ndv.w >> 16};
-        uint32_t dwl[8] = {dwv.x & 0xffffu, dwv.x >> 16, dwv.y & 0xffffu, dwv.y >> 16,
-                           dwv.z & 0xffffu, dwv.z >> 16, dwv.w & 0xffffu, dwv.w >> 16};
-        int pr[8] = {pr0.x, pr0.y, pr0.z, pr0.w, pr1.x, pr1.y, pr1.z, pr1.w};
-        const int mine_j = lane == (off >> 3) ? (off & 7) : -1;
-        if (mine_j >= 0) {
-          sm.prio[cell] = 0;   // video.py:140
-          sm.dw[cell] = 0;     // video.py:141
-        }
-        uint32_t bal[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j == mine_j) {
-            dwl[j] = 0;
-            pr[j] = 0;
-          }
-          bal[j] = __ballot_sync(kFull, (int)nd[j] - (int)dwl[j] < 0);   // video.py:283
-        }
-        int rank = 0, n_cand = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          rank += __popc(bal[j] & lt_mask);
-          n_cand += __popc(bal[j]);
-        }
+        // ---- _compute_error (video.py:275-301) -------------------------------------------
         if (pos_py + n_cand + 2 > 624 && mt_seen < mt_issued) {
           // the draws of this opcode reach into the block still being twisted
           const long long c0 = clock64();
@@ -616,17 +699,15 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         }
         // nonces of the (up to two) re-queue draws that follow the candidates' (:173-178)
         const uint32_t push_nonce0 = nonces[n_cand], push_nonce1 = nonces[n_cand + 1];
-        // every candidate draws one getrandbits(8), in ascending offset order (:290-293)
+        // every candidate draws one getrandbits(8), in ascending offset order (:290-293);
+        // only those with a live priority compete (:159)
         uint32_t key[8];
+        const uint32_t use8 = m8 & e8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const bool c = (bal[j] >> lane) & 1u;
-          const uint32_t nonce = nonces[rank];
-          const int delta = (int)nd[j] - (int)dwl[j];
-          const uint32_t k =
-              ((uint32_t)(delta + 32768) << 16) | (nonce << 8) | (uint32_t)(8 * lane + j);
-          key[j] = (c && pr[j] != 0) ? k : 0xffffffffu;   // video.py:159
-          rank += c ? 1 : 0;
+          const uint32_t nonce = nonces[rank + __popc(m8 & ((1u << j) - 1u))];
+          const uint32_t k = (khi[j] << 16) | (nonce << 8) | (uint32_t)(8 * lane + j);
+          key[j] = ((use8 >> j) & 1u) ? k : 0xffffffffu;
         }
         // two smallest of the lane's keys (keys are distinct: the offset is in them)
         uint32_t lo[4], hi[4];
@@ -654,6 +735,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         }
         const int push1 = p1 != 0, push2 = p2 != 0;
         if (lane == 0) {
+          sm.prio[cell] = 0;   // video.py:140
+          sm.dw[cell] = 0;     // video.py:141
           if (b1 != 0xffffffffu) sm.prio[page * 256 + o1] = (int32_t)p1;   // video.py:170
           if (b2 != 0xffffffffu) sm.prio[page * 256 + o2] = (int32_t)p2;
           if (push1)   // video.py:173-178
@@ -677,6 +760,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           rec.y |= (uint32_t)((emitted + 1) & 255) << 24;
           reinterpret_cast<volatile unsigned long long*>(sm.opq)[emitted % kOpQueue] =
               ((unsigned long long)rec.y << 32) | rec.x;
+          // the priorities above are in place: later front-end reads see this opcode
+          if (!heap_done) sm.b_done = r;
         }
         n_pushed += push1 + push2;
         pos_py += n_cand + push1 + push2;
@@ -699,8 +784,84 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         __threadfence_block();
         sm.stop = 1;
       }
-    } else if (warp != kTwistWarp && warp != kApplyWarp) {
-      for (int e = producer_idx; e < n_first; e += kProducers) {
+    } else if (warp == kDecideWarp - 1 || warp == kDecideWarp - 2) {
+      // ---- front end: records r = f, f + 2, ... ----------------------------------------
+      const int f = kDecideWarp - 1 - warp;
+      for (int r = f;; r += kFronts) {
+        // my turn to pop, with room in the record ring?
+        bool quit = false;
+        while (true) {
+          if (sm.stop) {
+            quit = true;
+            break;
+          }
+          if (sm.pop_turn == r && r < sm.b_done + kRecRing) break;
+          __nanosleep(20);
+        }
+        if (quit) break;
+        const int rs = r % kRecRing;
+        const int e = probe(sm.pop_cursor);
+        if (e < 0) {
+          // heap exhausted: tell the decision warp, and let the other front end see it too
+          if (lane == 0) {
+            sm.rec_hdr[rs][0] = kEndOfHeap;
+            rtags[rs] = (uint32_t)r;
+            sm.pop_turn = r + 1;
+          }
+          break;
+        }
+        const int cell = (int)(sm.keys[e] & 0x1fffu);
+        const int seen = sm.b_done;      // BEFORE the page is read
+        if (lane == 0) {
+          sm.pop_cursor = e + 1;
+          sm.pop_turn = r + 1;
+        }
+        // the row of this entry, from the producers.  If the cell has been zeroed since the
+        // probe (by an opcode decided meanwhile) nobody may ever score it: hand over a
+        // dead record, which the decision warp drops like the pop-and-skip it stands for.
+        const int slot = e % kRing;
+        uint32_t tag = 0;
+        bool dead = false;
+        while (true) {
+          if (reinterpret_cast<volatile int32_t*>(sm.prio)[cell] == 0) {
+            dead = true;
+            break;
+          }
+          tag = tags[slot];
+          if ((tag >> 8) == (uint32_t)e) break;
+          if (sm.stop) {
+            quit = true;
+            break;
+          }
+        }
+        if (quit) break;
+        if (dead) {
+          if (lane == 0) {
+            *reinterpret_cast<uint4*>(sm.rec_hdr[rs]) =
+                make_uint4((uint32_t)e, (uint32_t)cell, 0u, kDeadRecord);
+            rtags[rs] = (uint32_t)r;
+          }
+          continue;
+        }
+        asm volatile("" ::: "memory");
+        uint32_t khi[8], m8, e8;
+        int rank, n_cand;
+        digest(cell, sm.ring_row[slot], khi, m8, e8, rank, n_cand);
+        reinterpret_cast<uint4*>(sm.rec_khi[rs])[lane] =
+            make_uint4(khi[0] | (khi[1] << 16), khi[2] | (khi[3] << 16), khi[4] | (khi[5] << 16),
+                       khi[6] | (khi[7] << 16));
+        sm.rec_lane[rs][lane] = m8 | (e8 << 8) | ((uint32_t)rank << 16);
+        if (lane == 0)
+          *reinterpret_cast<uint4*>(sm.rec_hdr[rs]) =
+              make_uint4((uint32_t)e, (uint32_t)cell | ((tag & 0xffu) << 16), (uint32_t)n_cand,
+                         (uint32_t)seen);
+        __syncwarp();
+        if (lane == 0) rtags[rs] = (uint32_t)r;
+      }
+    } else if (warp < kProducers) {
+      // ---- producers: entries 2p, 2p+1 (mod 2 * kProducers), two rows in flight ----------
+      for (int e0 = 2 * warp; e0 < n_first; e0 += 2 * kProducers) {
+        const int e1 = e0 + 1;
         bool quit = false;
         while (true) {
           int h = 0, st = 0;
@@ -714,21 +875,29 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             quit = true;
             break;
           }
-          if (e < h + kRing) break;
+          if (e1 < h + kRing) break;
           __nanosleep(100);
         }
         if (quit) break;
-        const int cell = (int)(sm.keys[e] & 0x1fffu);
-        int alive = 0;
-        if (lane == 0) alive = reinterpret_cast<volatile int32_t*>(sm.prio)[cell];
-        alive = __shfl_sync(kFull, alive, 0);
-        if (alive == 0) continue;
-        const int slot = e % kRing;
-        const uint32_t content = __ldg(tmem + cell);
-        score_row<MODE>(tp + (cell >> 8) * 128, table, content, is_aux, lane, sm.ring_row[slot]);
+        const int cell0 = (int)(sm.keys[e0] & 0x1fffu);
+        const int cell1 = e1 < n_first ? (int)(sm.keys[e1] & 0x1fffu) : cell0;
+        const volatile int32_t* vprio = reinterpret_cast<volatile int32_t*>(sm.prio);
+        const bool alive0 = vprio[cell0] != 0;
+        const bool alive1 = e1 < n_first && vprio[cell1] != 0;
+        uint32_t c0 = 0, c1 = 0;
+        if (alive0) c0 = __ldg(tmem + cell0);
+        if (alive1) c1 = __ldg(tmem + cell1);
+        if (alive0)
+          score_row<MODE>(tp + (cell0 >> 8) * 128, table, c0, is_aux, lane,
+                          sm.ring_row[e0 % kRing]);
+        if (alive1)
+          score_row<MODE>(tp + (cell1 >> 8) * 128, table, c1, is_aux, lane,
+                          sm.ring_row[e1 % kRing]);
         __syncwarp();
-        if (lane == 0)   // after __syncwarp: every lane's row stores are ordered before this
-          reinterpret_cast<volatile uint32_t*>(sm.ring_tag)[slot] = ((uint32_t)e << 8) | content;
+        if (lane == 0) {   // after __syncwarp: every lane's row stores are ordered before this
+          if (alive0) tags[e0 % kRing] = ((uint32_t)e0 << 8) | c0;
+          if (alive1) tags[e1 % kRing] = ((uint32_t)e1 << 8) | c1;
+        }
       }
     } else if (warp == kApplyWarp) {
       // applier: Bitmap.apply for (off, o1, o2) of each record, in emission order.
@@ -757,7 +926,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           }
         }
       }
-    } else {
+    } else if (warp == kTwistWarp) {
       int done = 0;
       while (true) {
         int req = 0, st = 0;
