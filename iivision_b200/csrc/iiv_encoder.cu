@@ -63,7 +63,7 @@ struct Smem {
   int32_t prio[kCells];        // update_priority of the active bank
   uint16_t dw[kCells];         // local diff_weights (video.py:109-111)
   uint32_t mt_np[2][624];      // stream N, ping-pong
-  uint32_t mt_py[2][624];      // stream P: current block and its successor
+  uint32_t mt_py[3][624];      // stream P: current block and its two successors (ring)
   uint64_t wmin64[8];
   int32_t scan[kThreads / 32];
   uint32_t hist[kThreads / 32][257];   // per-warp digit histograms of the heap select
@@ -75,9 +75,9 @@ struct Smem {
   alignas(16) uint16_t ring_row[kRing + 1][256];
   uint32_t ring_tag[kRing];       // sorted-array index the slot holds
   // top byte of the tempered words of stream P (= getrandbits(8), video.py:178, :291):
-  // slot p holds the block of parity p, slot 2 repeats slot 0, so that the bytes of
-  // the current block and of its successor are always contiguous from p * 624
-  uint8_t py_nonce[3 * 624 + 16];
+  // slot s < 3 holds the block whose number is s (mod 3), slot 3 repeats slot 0, so that
+  // the bytes of the current block and of its successor are always contiguous
+  uint8_t py_nonce[4 * 624 + 16];
   // emitted records waiting for warp 6 to apply their stores; byte 7 of a record
   // carries (sequence number & 255), so one 64-bit store publishes it
   unsigned long long opq[kOpQueue];
@@ -133,13 +133,13 @@ __device__ __forceinline__ uint4 lds_v4(const void* p) {
 }
 
 // getrandbits(8) bytes of one block of stream P into its slot(s) of py_nonce.
-__device__ __forceinline__ void fill_nonces(const uint32_t* __restrict__ block, int parity,
+__device__ __forceinline__ void fill_nonces(const uint32_t* __restrict__ block, int slot,
                                             uint8_t* __restrict__ py_nonce, int idx,
                                             int stride) {
   for (int k = idx; k < 624; k += stride) {
     const uint8_t b = (uint8_t)(mt_temper(block[k]) >> 24);
-    py_nonce[parity * 624 + k] = b;
-    if (parity == 0) py_nonce[2 * 624 + k] = b;
+    py_nonce[slot * 624 + k] = b;
+    if (slot == 0) py_nonce[3 * 624 + k] = b;
   }
 }
 
@@ -242,11 +242,16 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
   int np_cur = 0;                 // which ping-pong buffer holds stream N
   int pos_np = (int)g_mt_np[624]; // 0..624
   int pos_py = (int)g_mt_py[624];
-  int py_cur = 0;                 // mt_py[py_cur] current block, [py_cur^1] next
+  // Three blocks of stream P stay resident (ring of buffers, slot = block number mod 3):
+  // when the position moves on to the next block the twister refills the freed buffer a
+  // whole block (~8 opcodes) before it can be needed.
+  int py_cur = 0;                 // slot of the current block
   __syncthreads();
-  twist(sm.mt_py[py_cur], sm.mt_py[py_cur ^ 1]);
+  twist(sm.mt_py[0], sm.mt_py[1]);
+  twist(sm.mt_py[1], sm.mt_py[2]);
   fill_nonces(sm.mt_py[0], 0, sm.py_nonce, t, kThreads);
   fill_nonces(sm.mt_py[1], 1, sm.py_nonce, t, kThreads);
+  fill_nonces(sm.mt_py[2], 2, sm.py_nonce, t, kThreads);
   int error_flags = 0;
 
   uint8_t* op_out = opcodes + (size_t)clip * total_budget * 8;
@@ -275,36 +280,52 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     const int cell0 = t * 32;
     const int page_a = t >> 3;
     const int colbase = page_a * 128 + (t & 7) * 16;
+    // All loads of a stage are issued before anything waits on them: 8 x 16-byte target
+    // words and priorities first, then the 32 table gathers.
     uint32_t dwv[32];
+    {
+      ulonglong2 g2[8];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const uint64_t s = sm.src[colbase + c];
-      const uint64_t g = __ldg(tp + colbase + c);
+      for (int c = 0; c < 8; ++c)
+        g2[c] = __ldg(reinterpret_cast<const ulonglong2*>(tp + colbase) + c);
+      uint32_t gidx[32];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int o = byte_offset<MODE>(half, is_aux);
-        const uint32_t x = mask_shift<MODE>(s, o), y = mask_shift<MODE>(g, o);
-        const int offset = (t & 7) * 32 + 2 * c + half;
-        uint32_t d = 0;
-        if (!is_hole(offset))  // video.py:111
-          d = __ldg(table + ((size_t)o << (2 * M::kBits)) + ((size_t)x << M::kBits) + y);
-        dwv[2 * c + half] = d;
+      for (int c = 0; c < 16; ++c) {
+        const uint64_t s = sm.src[colbase + c];
+        const uint64_t g = (c & 1) ? g2[c >> 1].y : g2[c >> 1].x;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int o = byte_offset<MODE>(half, is_aux);
+          const uint32_t x = mask_shift<MODE>(s, o), y = mask_shift<MODE>(g, o);
+          gidx[2 * c + half] = ((uint32_t)o << (2 * M::kBits)) + (x << M::kBits) + y;
+        }
       }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) dwv[k] = __ldg(table + gidx[k]);
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (is_hole((t & 7) * 32 + k)) dwv[k] = 0;   // video.py:111
     }
     int64_t prio_sum = 0;
     int nz = 0;
     uint32_t nzmask = 0;
+    {
+      int4 pv[8];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      int32_t p = g_prio[cell0 + k];
-      prio_sum += p;
-      if (dwv[k] == 0) p = 0;          // video.py:115
-      p += (int32_t)dwv[k];            // video.py:116
-      sm.prio[cell0 + k] = p;
-      sm.dw[cell0 + k] = (uint16_t)dwv[k];
-      if (p != 0) {
-        ++nz;
-        nzmask |= 1u << k;
+      for (int q = 0; q < 8; ++q) pv[q] = reinterpret_cast<const int4*>(g_prio + cell0)[q];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int4 v = pv[k >> 2];
+        int32_t p = (k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w;
+        prio_sum += p;
+        if (dwv[k] == 0) p = 0;          // video.py:115
+        p += (int32_t)dwv[k];            // video.py:116
+        sm.prio[cell0 + k] = p;
+        sm.dw[cell0 + k] = (uint16_t)dwv[k];
+        if (p != 0) {
+          ++nz;
+          nzmask |= 1u << k;
+        }
       }
     }
     // block-wide sums: exclusive scan of nz, total of prio_sum.
@@ -492,17 +513,17 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     //       (only stores to that page change what was read); then the warp re-digests
     //       the entry itself.  It draws the nonces, picks the two best offsets, updates
     //       priorities, re-queues, publishes the opcode: shared memory + shuffles only.
-    //   applier (warp 4)  commits the stores of every published opcode to the source
+    //   applier (warp 3)  commits the stores of every published opcode to the source
     //       bitmap and memory map (Bitmap.apply), in order.  Nothing in phase B reads
     //       the source, so this is off the chain.
-    //   twister (warp 3)  prepares the next MT19937 block of stream P in the background.
+    //   twister (warp 4)  prepares the next MT19937 block of stream P in the background.
     // A cell whose priority is already 0 is skipped by everyone alike: priorities only
     // ever fall to 0 inside a segment (video.py:140, :159-170).
     // The issue arbiter favours the highest warp id of a scheduler and a spinning warp
     // is nearly always eligible, hence the decision warp is 7 and shares its scheduler
-    // (warp id % 4) with the mostly idle twister; helper loops back off with nanosleep.
+    // (warp id % 4) with the single-lane applier; helper loops back off with nanosleep.
     constexpr uint32_t kFull = 0xffffffffu;
-    constexpr int kDecideWarp = 7, kTwistWarp = 3, kApplyWarp = 4;
+    constexpr int kDecideWarp = 7, kTwistWarp = 4, kApplyWarp = 3;
     constexpr uint32_t kEndOfHeap = 0xffffffffu, kDeadRecord = 0xffffffffu;
     if (t < kRing) sm.ring_tag[t] = 0xffffffffu;
     if (t < kRecRing) sm.rec_tag[t] = 0xffffffffu;
@@ -590,16 +611,22 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       bool heap_done = false;    // sorted heap exhausted: re-queued cells only
       uint32_t hist = 0xffu;     // lane l < 16: page of the record r' = l (mod 16) decided last
       while (emitted < budget) {
-        // ---- stream P bookkeeping: two resident 624-word blocks ----------------------
+        // ---- stream P bookkeeping: three resident 624-word blocks ----------------------
         // (every lane polls the same shared word in one broadcast load, so the loop
         // conditions below are warp-uniform)
         if (pos_py > 624) {
-          while (mt_seen < mt_issued) mt_seen = sm.mt_done;
-          py_cur ^= 1;
+          // the refill asked for one block ago must be in before its buffer can be read
+          if (mt_seen < mt_issued) {
+            const long long c0 = clock64();
+            while (mt_seen < mt_issued) mt_seen = sm.mt_done;
+            wait_misc += clock64() - c0;
+          }
+          py_cur = py_cur == 2 ? 0 : py_cur + 1;
           pos_py -= 624;
           ++mt_issued;
           if (lane == 0) {
-            sm.mt_src = py_cur;
+            // blocks cur, cur+1 are resident; cur+2 is made from cur+1 into the freed slot
+            sm.mt_src = py_cur == 2 ? 0 : py_cur + 1;
             __threadfence_block();
             sm.mt_req = mt_issued;
           }
@@ -691,12 +718,6 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         if (MODE == IIV_MODE_DHGR && content >= 0x80u) error_flags |= 1;  // :137
 
         // ---- _compute_error (video.py:275-301) -------------------------------------------
-        if (pos_py + n_cand + 2 > 624 && mt_seen < mt_issued) {
-          // the draws of this opcode reach into the block still being twisted
-          const long long c0 = clock64();
-          while (mt_seen < mt_issued) mt_seen = sm.mt_done;
-          wait_misc += clock64() - c0;
-        }
         // nonces of the (up to two) re-queue draws that follow the candidates' (:173-178)
         const uint32_t push_nonce0 = nonces[n_cand], push_nonce1 = nonces[n_cand + 1];
         // every candidate draws one getrandbits(8), in ascending offset order (:290-293);
@@ -939,8 +960,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         if (req > done) {
           __threadfence_block();
           const int src = sm.mt_src;
-          warp_twist(sm.mt_py[src], sm.mt_py[src ^ 1], lane);
-          fill_nonces(sm.mt_py[src ^ 1], src ^ 1, sm.py_nonce, lane, 32);
+          const int dst = src == 2 ? 0 : src + 1;
+          warp_twist(sm.mt_py[src], sm.mt_py[dst], lane);
+          fill_nonces(sm.mt_py[dst], dst, sm.py_nonce, lane, 32);
           ++done;
           __threadfence_block();
           __syncwarp();
@@ -989,7 +1011,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
 
   // ---- store persistent state ----------------------------------------------------
   if (pos_py > 624) {  // normalise so that (state, pos) is a legal MT19937 state
-    py_cur ^= 1;
+    py_cur = py_cur == 2 ? 0 : py_cur + 1;
     pos_py -= 624;
   }
   for (int k = t; k < kCols; k += kThreads) g_packed[k] = sm.src[k];
