@@ -82,9 +82,12 @@ struct Smem {
   // carries (sequence number & 255), so one 64-bit store publishes it
   unsigned long long opq[kOpQueue];
   // front-end records: a popped heap entry with its candidate analysis (see phase B)
-  alignas(16) uint16_t rec_khi[kRecRing][256];   // per offset: (delta + 32768) & 0xffff
-  uint32_t rec_lane[kRecRing][32];               // per lane: cand bits | elig bits << 8 | rank << 16
-  uint32_t rec_hdr[kRecRing][4];                 // entry, cell | content << 16, n_cand, b_done seen
+  // contenders of a record: the competing candidates (delta < 0, priority != 0) whose
+  // delta is one of the two smallest -- only they can be among the two winners, whatever
+  // the nonces turn out to be.  (delta + 32768) << 16 | nonce rank << 8 | offset.
+  uint32_t rec_cont[kRecRing][32];
+  // entry, cell | content << 16, n_cand | n_contenders << 16, b_done seen
+  alignas(16) uint32_t rec_hdr[kRecRing][4];
   uint32_t rec_tag[kRecRing];                    // record number the slot holds
   volatile int pop_turn;          // next record number to be popped
   volatile int pop_cursor;        // sorted-heap cursor of that pop
@@ -110,14 +113,49 @@ __device__ __forceinline__ void twist(const uint32_t* __restrict__ s,
 }
 
 // The same generation step done by a single warp (phase B helper warp).
+// Also stores getrandbits(8) = top byte of each tempered new word into the block's
+// slot(s) of py_nonce (slot s < 3 holds block numbers s mod 3; slot 3 repeats slot 0).
 __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
-                                           uint32_t* __restrict__ d, int lane) {
-  for (int t = lane; t < 227; t += 32) d[t] = mt_mix(s[t], s[t + 1], s[t + 397]);
+                                           uint32_t* __restrict__ d, int lane, int slot,
+                                           uint8_t* __restrict__ py_nonce) {
+  uint8_t* nb = py_nonce + slot * 624;
+  uint8_t* nb2 = py_nonce + (slot == 0 ? 3 * 624 : slot * 624);
+  // three dependent sweeps of 227 / 227 / 170 words; inside a sweep every word is
+  // independent, so the loops are fully unrolled to keep 8 loads in flight per lane
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int t = lane + 32 * k;
+    if (t < 227) {
+      const uint32_t w = mt_mix(s[t], s[t + 1], s[t + 397]);
+      d[t] = w;
+      nb[t] = nb2[t] = (uint8_t)(mt_temper(w) >> 24);
+    }
+  }
   __syncwarp();
-  for (int t = lane; t < 227; t += 32) d[227 + t] = mt_mix(s[227 + t], s[228 + t], d[t]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int t = lane + 32 * k;
+    if (t < 227) {
+      const uint32_t w = mt_mix(s[227 + t], s[228 + t], d[t]);
+      d[227 + t] = w;
+      nb[227 + t] = nb2[227 + t] = (uint8_t)(mt_temper(w) >> 24);
+    }
+  }
   __syncwarp();
-  for (int t = lane; t < 169; t += 32) d[454 + t] = mt_mix(s[454 + t], s[455 + t], d[227 + t]);
-  if (lane == 0) d[623] = mt_mix(s[623], d[0], d[396]);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int t = lane + 32 * k;
+    if (t < 169) {
+      const uint32_t w = mt_mix(s[454 + t], s[455 + t], d[227 + t]);
+      d[454 + t] = w;
+      nb[454 + t] = nb2[454 + t] = (uint8_t)(mt_temper(w) >> 24);
+    }
+  }
+  if (lane == 0) {
+    const uint32_t w = mt_mix(s[623], d[0], d[396]);
+    d[623] = w;
+    nb[623] = nb2[623] = (uint8_t)(mt_temper(w) >> 24);
+  }
   __syncwarp();
 }
 
@@ -136,6 +174,7 @@ __device__ __forceinline__ uint4 lds_v4(const void* p) {
 __device__ __forceinline__ void fill_nonces(const uint32_t* __restrict__ block, int slot,
                                             uint8_t* __restrict__ py_nonce, int idx,
                                             int stride) {
+#pragma unroll 4
   for (int k = idx; k < 624; k += stride) {
     const uint8_t b = (uint8_t)(mt_temper(block[k]) >> 24);
     py_nonce[slot * 624 + k] = b;
@@ -499,7 +538,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     // The opcode loop is a chain -- each opcode's nonces start where the previous
     // one's ended, and its stores change the priorities the next pop sees -- so it is
     // cut into stages run by specialised warps, none of which crosses a block barrier:
-    //   producers (warps 0-2)  run ahead along the sorted heap and score the row of
+    //   producers (warps 1-3)  run ahead along the sorted heap and score the row of
     //       new diffs of each upcoming entry (two dependent global loads: target word,
     //       table gather) into a ring in shared memory, two entries in flight per warp.
     //       A row depends on the target frame and the content byte only, never on the
@@ -513,17 +552,18 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     //       (only stores to that page change what was read); then the warp re-digests
     //       the entry itself.  It draws the nonces, picks the two best offsets, updates
     //       priorities, re-queues, publishes the opcode: shared memory + shuffles only.
-    //   applier (warp 3)  commits the stores of every published opcode to the source
+    //   applier (warp 4)  commits the stores of every published opcode to the source
     //       bitmap and memory map (Bitmap.apply), in order.  Nothing in phase B reads
     //       the source, so this is off the chain.
-    //   twister (warp 4)  prepares the next MT19937 block of stream P in the background.
+    //   twister (warp 0)  prepares the next MT19937 block of stream P in the background.
     // A cell whose priority is already 0 is skipped by everyone alike: priorities only
     // ever fall to 0 inside a segment (video.py:140, :159-170).
     // The issue arbiter favours the highest warp id of a scheduler and a spinning warp
     // is nearly always eligible, hence the decision warp is 7 and shares its scheduler
-    // (warp id % 4) with the single-lane applier; helper loops back off with nanosleep.
+    // (warp id % 4) with a producer, which mostly waits on global loads; the applier and
+    // the twister share scheduler 0; helper loops back off with nanosleep.
     constexpr uint32_t kFull = 0xffffffffu;
-    constexpr int kDecideWarp = 7, kTwistWarp = 4, kApplyWarp = 3;
+    constexpr int kDecideWarp = 7, kTwistWarp = 3, kApplyWarp = 4;
     constexpr uint32_t kEndOfHeap = 0xffffffffu, kDeadRecord = 0xffffffffu;
     if (t < kRing) sm.ring_tag[t] = 0xffffffffu;
     if (t < kRecRing) sm.rec_tag[t] = 0xffffffffu;
@@ -544,7 +584,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     int emitted = 0, py_words = 0;
     bool out_of_work = false;
     const long long clk_b = clock64();
-    long long wait_rows = 0, wait_misc = 0;   // decision-warp stall cycles (diagnostics)
+    long long wait_rows = 0, wait_misc = 0, wait_mt = 0;   // decision-warp stall cycles (diagnostics)
     volatile uint32_t* tags = sm.ring_tag;
     volatile uint32_t* rtags = sm.rec_tag;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -619,7 +659,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           if (mt_seen < mt_issued) {
             const long long c0 = clock64();
             while (mt_seen < mt_issued) mt_seen = sm.mt_done;
-            wait_misc += clock64() - c0;
+            wait_mt += clock64() - c0;
           }
           py_cur = py_cur == 2 ? 0 : py_cur + 1;
           pos_py -= 624;
@@ -633,8 +673,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         }
         const uint8_t* nonces = sm.py_nonce + py_cur * 624 + pos_py;
 
-        int cell, slot, rank, n_cand;
-        uint32_t content, m8, e8, khi[8];
+        int cell, slot, rank, n_cand, n_cont = -1;   // n_cont < 0: evaluate all 256 offsets
+        uint32_t content, m8, e8, khi[8], cont = 0;
         bool have = false;
         if (!heap_done) {
           // ---- next record of the front ends -------------------------------------------
@@ -657,21 +697,15 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             if (lane == 0) sm.head = e;
             // valid unless a record decided after the front end's read hit this page
             const int seen = (int)hdr.w;
-            const bool in_window = lane < 16 && ((r - 1 - lane) & 15) < r - seen;
+            const bool in_window = (lane < 16) & (((r - 1 - lane) & 15) < r - seen);
             const bool conflict =
                 __ballot_sync(kFull, in_window && hist == (uint32_t)(cell >> 8)) != 0;
             if (hdr.w == kDeadRecord) {
               // dropped by the front end: the cell is zero
-            } else if (!conflict) {
-              const uint4 kv = lds_v4(&sm.rec_khi[rs][8 * lane]);
-              const uint32_t li = reinterpret_cast<volatile uint32_t*>(sm.rec_lane[rs])[lane];
-              khi[0] = kv.x & 0xffffu; khi[1] = kv.x >> 16; khi[2] = kv.y & 0xffffu;
-              khi[3] = kv.y >> 16; khi[4] = kv.z & 0xffffu; khi[5] = kv.z >> 16;
-              khi[6] = kv.w & 0xffffu; khi[7] = kv.w >> 16;
-              m8 = li & 0xffu;
-              e8 = (li >> 8) & 0xffu;
-              rank = (int)(li >> 16);
-              n_cand = (int)hdr.z;
+            } else if (!conflict && (hdr.z >> 16) <= 32u) {
+              n_cand = (int)(hdr.z & 0xffffu);
+              n_cont = (int)(hdr.z >> 16);
+              cont = reinterpret_cast<volatile uint32_t*>(sm.rec_cont[rs])[lane];
               have = true;
             } else if (sm.prio[cell] != 0) {
               digest(cell, sm.ring_row[slot], khi, m8, e8, rank, n_cand);
@@ -721,28 +755,41 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         // nonces of the (up to two) re-queue draws that follow the candidates' (:173-178)
         const uint32_t push_nonce0 = nonces[n_cand], push_nonce1 = nonces[n_cand + 1];
         // every candidate draws one getrandbits(8), in ascending offset order (:290-293);
-        // only those with a live priority compete (:159)
-        uint32_t key[8];
-        const uint32_t use8 = m8 & e8;
+        // only those with a live priority compete (:159); the two smallest (delta, nonce,
+        // offset) win
+        uint32_t b1, b2;
+        if (n_cont >= 0) {
+          // front-end record: lane i holds contender i
+          uint32_t key = 0xffffffffu;
+          if (lane < n_cont)
+            key = (cont & 0xffff00ffu) | ((uint32_t)nonces[(cont >> 8) & 0xffu] << 8);
+          b1 = __reduce_min_sync(kFull, key);
+          b2 = __reduce_min_sync(kFull, key == b1 ? 0xffffffffu : key);
+        } else {
+          uint32_t key[8];
+          const uint32_t use8 = m8 & e8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t nonce = nonces[rank + __popc(m8 & ((1u << j) - 1u))];
-          const uint32_t k = (khi[j] << 16) | (nonce << 8) | (uint32_t)(8 * lane + j);
-          key[j] = ((use8 >> j) & 1u) ? k : 0xffffffffu;
-        }
-        // two smallest of the lane's keys (keys are distinct: the offset is in them)
-        uint32_t lo[4], hi[4];
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t nonce = nonces[rank + __popc(m8 & ((1u << j) - 1u))];
+            const uint32_t k = (khi[j] << 16) | (nonce << 8) | (uint32_t)(8 * lane + j);
+            key[j] = ((use8 >> j) & 1u) ? k : 0xffffffffu;
+          }
+          // two smallest of the lane's keys (keys are distinct: the offset is in them)
+          uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          lo[q] = min(key[2 * q], key[2 * q + 1]);
-          hi[q] = max(key[2 * q], key[2 * q + 1]);
+          for (int q = 0; q < 4; ++q) {
+            lo[q] = min(key[2 * q], key[2 * q + 1]);
+            hi[q] = max(key[2 * q], key[2 * q + 1]);
+          }
+          const uint32_t lo01 = min(lo[0], lo[1]),
+                         hi01 = min(max(lo[0], lo[1]), min(hi[0], hi[1]));
+          const uint32_t lo23 = min(lo[2], lo[3]),
+                         hi23 = min(max(lo[2], lo[3]), min(hi[2], hi[3]));
+          const uint32_t best1 = min(lo01, lo23);
+          const uint32_t best2 = min(max(lo01, lo23), min(hi01, hi23));
+          b1 = __reduce_min_sync(kFull, best1);
+          b2 = __reduce_min_sync(kFull, best1 == b1 ? best2 : best1);
         }
-        const uint32_t lo01 = min(lo[0], lo[1]), hi01 = min(max(lo[0], lo[1]), min(hi[0], hi[1]));
-        const uint32_t lo23 = min(lo[2], lo[3]), hi23 = min(max(lo[2], lo[3]), min(hi[2], hi[3]));
-        const uint32_t best1 = min(lo01, lo23);
-        const uint32_t best2 = min(max(lo01, lo23), min(hi01, hi23));
-        const uint32_t b1 = __reduce_min_sync(kFull, best1);
-        const uint32_t b2 = __reduce_min_sync(kFull, best1 == b1 ? best2 : best1);
         // byte_pair_difference of the accepted offsets (video.py:166) = their new diff
         uint32_t p1 = 0, p2 = 0;
         int o1 = off, o2 = off;
@@ -794,7 +841,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       if (lane == 0) {
         sm.final_emitted = emitted;
         sm.wmin64[0] = (uint64_t)wait_rows;
-        sm.wmin64[1] = (uint64_t)wait_misc;
+        sm.wmin64[1] = (uint64_t)(wait_misc + wait_mt);
         sm.wmin64[2] = (uint64_t)(clock64() - clk_b);
         sm.scan[0] = emitted;
         sm.scan[1] = out_of_work ? 1 : 0;
@@ -848,6 +895,11 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             dead = true;
             break;
           }
+          // Flow control of the row ring: the producers may fill [head, head + kRing).
+          // Once every earlier record has been decided this entry is the oldest one in
+          // use, however many dead entries precede it -- move the window up to it, or
+          // nobody would ever score it.
+          if (lane == 0 && sm.b_done == r) sm.head = e;
           tag = tags[slot];
           if ((tag >> 8) == (uint32_t)e) break;
           if (sm.stop) {
@@ -868,14 +920,45 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         uint32_t khi[8], m8, e8;
         int rank, n_cand;
         digest(cell, sm.ring_row[slot], khi, m8, e8, rank, n_cand);
-        reinterpret_cast<uint4*>(sm.rec_khi[rs])[lane] =
-            make_uint4(khi[0] | (khi[1] << 16), khi[2] | (khi[3] << 16), khi[4] | (khi[5] << 16),
-                       khi[6] | (khi[7] << 16));
-        sm.rec_lane[rs][lane] = m8 | (e8 << 8) | ((uint32_t)rank << 16);
+        // Whatever the nonces, the two winners have one of the two smallest deltas among
+        // the competing candidates: pass only those on (with their nonce ranks).
+        const uint32_t use8 = m8 & e8;
+        uint32_t lane_min = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if ((use8 >> j) & 1u) lane_min = min(lane_min, khi[j]);
+        const uint32_t d1 = __reduce_min_sync(kFull, lane_min);
+        uint32_t lane_min2 = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (((use8 >> j) & 1u) && khi[j] > d1) lane_min2 = min(lane_min2, khi[j]);
+        const uint32_t d2 = __reduce_min_sync(kFull, lane_min2);
+        uint32_t c8 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (((use8 >> j) & 1u) && khi[j] <= d2) c8 |= 1u << j;
+        const int mine = __popc(c8);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += v;
+        }
+        const int n_cont = __shfl_sync(kFull, incl, 31);
+        if (n_cont <= 32) {
+          int at = incl - mine;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if ((c8 >> j) & 1u) {
+              const uint32_t nrank = (uint32_t)(rank + __popc(m8 & ((1u << j) - 1u)));
+              sm.rec_cont[rs][at++] = (khi[j] << 16) | (nrank << 8) | (uint32_t)(8 * lane + j);
+            }
+          }
+        }
         if (lane == 0)
-          *reinterpret_cast<uint4*>(sm.rec_hdr[rs]) =
-              make_uint4((uint32_t)e, (uint32_t)cell | ((tag & 0xffu) << 16), (uint32_t)n_cand,
-                         (uint32_t)seen);
+          *reinterpret_cast<uint4*>(sm.rec_hdr[rs]) = make_uint4(
+              (uint32_t)e, (uint32_t)cell | ((tag & 0xffu) << 16),
+              (uint32_t)n_cand | ((uint32_t)min(n_cont, 0xffff) << 16), (uint32_t)seen);
         __syncwarp();
         if (lane == 0) rtags[rs] = (uint32_t)r;
       }
@@ -921,30 +1004,54 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         }
       }
     } else if (warp == kApplyWarp) {
-      // applier: Bitmap.apply for (off, o1, o2) of each record, in emission order.
-      // Re-applying an offset that repeats offsets[0] is idempotent.
-      if (lane == 0) {
-        int applied = 0;
-        volatile unsigned long long* q = sm.opq;
-        while (true) {
-          const unsigned long long raw = q[applied % kOpQueue];
-          if ((uint32_t)(raw >> 56) == (uint32_t)((applied + 1) & 255) && raw != 0ull) {
-            const uint32_t rx = (uint32_t)raw, ry = (uint32_t)(raw >> 32);
-            const int page = (int)(rx & 0xffu) - 32;
-            const uint32_t content = (rx >> 8) & 0xffu;
-            const int off = (int)((rx >> 16) & 0xffu), o1 = (int)(rx >> 24);
-            const int o2 = (int)(ry & 0xffu);
-            apply_store<MODE>(sm.src, g_mem, page, off, is_aux, content);
-            if (o1 != off) apply_store<MODE>(sm.src, g_mem, page, o1, is_aux, content);
-            if (o2 != off) apply_store<MODE>(sm.src, g_mem, page, o2, is_aux, content);
-            ++applied;
-            sm.applied_pub = applied;
-          } else if (sm.stop) {
-            __threadfence_block();
-            if (applied >= sm.final_emitted) break;
-          } else {
-            __nanosleep(100);
+      // applier: Bitmap.apply for (off, o1, o2) of each published record.  Stores only
+      // interact inside a page (a packed word and its two neighbours), so lane i takes
+      // the i-th pending record and records of different pages are applied at once;
+      // records that share a page go in emission order, one per round.  Re-applying an
+      // offset that repeats offsets[0] is idempotent.
+      int applied = 0;
+      volatile unsigned long long* q = sm.opq;
+      while (true) {
+        const int idx = applied + lane;
+        const unsigned long long raw = q[idx % kOpQueue];
+        const bool ready = (uint32_t)(raw >> 56) == (uint32_t)((idx + 1) & 255) && raw != 0ull;
+        // the records form a prefix: lane i can only go if lanes < i are ready as well
+        const uint32_t rdy = __ballot_sync(kFull, ready);
+        const int n = __ffs(~rdy) - 1;          // length of the ready prefix (0..32; -1 -> 32)
+        const int count = n < 0 ? 32 : n;
+        if (count > 0) {
+          const bool mine = lane < count;
+          const uint32_t rx = (uint32_t)raw, ry = (uint32_t)(raw >> 32);
+          const int page = (int)(rx & 0xffu) - 32;
+          const uint32_t content = (rx >> 8) & 0xffu;
+          const int off = (int)((rx >> 16) & 0xffu), o1 = (int)(rx >> 24);
+          const int o2 = (int)(ry & 0xffu);
+          // lanes holding the same page, in lane (= emission) order
+          const uint32_t group = __match_any_sync(kFull, mine ? page : 64 + lane);
+          uint32_t pending = group;
+          while (__any_sync(kFull, mine && pending != 0)) {
+            if (mine && pending != 0 && (pending & ((1u << lane) - 1u)) == 0) {
+              apply_store<MODE>(sm.src, g_mem, page, off, is_aux, content);
+              if (o1 != off) apply_store<MODE>(sm.src, g_mem, page, o1, is_aux, content);
+              if (o2 != off) apply_store<MODE>(sm.src, g_mem, page, o2, is_aux, content);
+            }
+            __syncwarp();
+            // every group retires its lowest pending lane
+            pending &= pending - 1;
           }
+          applied += count;
+          if (lane == 0) sm.applied_pub = applied;
+        } else {
+          int st = 0, fin = 0;
+          if (lane == 0) {
+            st = sm.stop;                 // read before the count: stop is set last
+            __threadfence_block();
+            fin = sm.final_emitted;
+          }
+          st = __shfl_sync(kFull, st, 0);
+          fin = __shfl_sync(kFull, fin, 0);
+          if (st && applied >= fin) break;
+          __nanosleep(100);
         }
       }
     } else if (warp == kTwistWarp) {
@@ -961,8 +1068,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           __threadfence_block();
           const int src = sm.mt_src;
           const int dst = src == 2 ? 0 : src + 1;
-          warp_twist(sm.mt_py[src], sm.mt_py[dst], lane);
-          fill_nonces(sm.mt_py[dst], dst, sm.py_nonce, lane, 32);
+          warp_twist(sm.mt_py[src], sm.mt_py[dst], lane, dst, sm.py_nonce);
           ++done;
           __threadfence_block();
           __syncwarp();
@@ -1000,7 +1106,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       info[4] = (int64_t)(clk_b - clk_seg);        // cycles: score + heapify
       info[5] = (int64_t)sm.wmin64[2];             // cycles: opcode loop
       info[6] = (int64_t)sm.wmin64[0];             // consumer cycles waiting for rows
-      info[7] = (int64_t)sm.wmin64[1];             // consumer cycles waiting for MT / applier
+      info[7] = (int64_t)sm.wmin64[1];             // decision-warp cycles waiting for MT / applier
       if (out_of_work) g_flags[is_aux ? 1 : 0] = 1;   // video.py:189
     }
     op_out += (size_t)budget * 8;

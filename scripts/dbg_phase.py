@@ -18,7 +18,7 @@ for rep in range(3):
     _, info = ops.encode_clips("DHGR", st, tmem, tpacked, segs, table)
     torch.cuda.synchronize()
 info = info.cpu().numpy()[0]
-print("seg: emitted n_heap | total_A  score  keygen  select  sort | loop")
+print("seg: emitted n_heap | total_A | loop | wait_rows wait_mt wait_applier")
 for k in range(info.shape[0]):
     r = info[k]
-    print(k, r[0], r[2], "|", r[4], r[6] & 0xffffffff, r[6] >> 32, r[7] & 0xffffffff, r[7] >> 32, "|", r[5])
+    print(k, r[0], r[2], "|", r[4], "|", r[5], "|", r[6] & 0xffffffff, r[6] >> 32, "twist", r[7] & 0xffffffff, "fill", r[7] >> 32)
