@@ -74,6 +74,8 @@ struct Smem {
   // consumer's own (re-queued cells are scored on demand).
   alignas(16) uint16_t ring_row[kRing + 1][256];
   uint32_t ring_tag[kRing];       // sorted-array index the slot holds
+  uint32_t ring_lock[kRing];      // a producer is writing the slot
+  uint32_t ring_claim[kRing];     // 1 + newest entry that has written (or is writing) the slot
   // top byte of the tempered words of stream P (= getrandbits(8), video.py:178, :291):
   // slot s < 3 holds the block whose number is s (mod 3), slot 3 repeats slot 0, so that
   // the bytes of the current block and of its successor are always contiguous
@@ -186,6 +188,33 @@ __device__ __forceinline__ void fill_nonces(const uint32_t* __restrict__ block, 
 // (Bitmap._diff_weights_page with source = target, screen.py:453-494, 544): lane l
 // owns offsets 8l .. 8l+7, i.e. packed columns 4l .. 4l+3.  Screen holes (lanes 15
 // and 31) get 0xffff so that they are never candidates.
+template <int MODE>
+__device__ __forceinline__ uint4 score_row_regs(const uint64_t* __restrict__ tp_row,
+                                                const uint16_t* __restrict__ table,
+                                                uint32_t content, int is_aux, int lane) {
+  using M = Mode<MODE>;
+  uint4 packed_out = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  if ((lane & 15) != 15) {
+    const ulonglong2 w01 = __ldg(reinterpret_cast<const ulonglong2*>(tp_row) + 2 * lane);
+    const ulonglong2 w23 = __ldg(reinterpret_cast<const ulonglong2*>(tp_row) + 2 * lane + 1);
+    const uint64_t w[4] = {w01.x, w01.y, w23.x, w23.y};
+    uint32_t nd[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int o = byte_offset<MODE>(half, is_aux);
+        const uint32_t x = mask_shift<MODE>(masked_update<MODE>(o, w[q], content), o);
+        const uint32_t y = mask_shift<MODE>(w[q], o);
+        nd[2 * q + half] =
+            __ldg(table + ((size_t)o << (2 * M::kBits)) + ((size_t)x << M::kBits) + y);
+      }
+    packed_out = make_uint4(nd[0] | (nd[1] << 16), nd[2] | (nd[3] << 16),
+                            nd[4] | (nd[5] << 16), nd[6] | (nd[7] << 16));
+  }
+  return packed_out;
+}
+
 template <int MODE>
 __device__ __forceinline__ void score_row(const uint64_t* __restrict__ tp_row,
                                           const uint16_t* __restrict__ table,
@@ -565,7 +594,11 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr int kDecideWarp = 7, kTwistWarp = 3, kApplyWarp = 4;
     constexpr uint32_t kEndOfHeap = 0xffffffffu, kDeadRecord = 0xffffffffu;
-    if (t < kRing) sm.ring_tag[t] = 0xffffffffu;
+    if (t < kRing) {
+      sm.ring_tag[t] = 0xffffffffu;
+      sm.ring_lock[t] = 0;
+      sm.ring_claim[t] = 0;
+    }
     if (t < kRecRing) sm.rec_tag[t] = 0xffffffffu;
     if (t == 0) {
       sm.head = 0;
@@ -716,7 +749,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             ++r;
             if (!have) {
               __syncwarp();
-              if (lane == 0) sm.b_done = r;
+              if (lane == 0) {
+                __threadfence_block();
+                sm.b_done = r;
+              }
               continue;
             }
           }
@@ -829,6 +865,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           reinterpret_cast<volatile unsigned long long*>(sm.opq)[emitted % kOpQueue] =
               ((unsigned long long)rec.y << 32) | rec.x;
           // the priorities above are in place: later front-end reads see this opcode
+          __threadfence_block();
           if (!heap_done) sm.b_done = r;
         }
         n_pushed += push1 + push2;
@@ -873,6 +910,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           // heap exhausted: tell the decision warp, and let the other front end see it too
           if (lane == 0) {
             sm.rec_hdr[rs][0] = kEndOfHeap;
+            __threadfence_block();
             rtags[rs] = (uint32_t)r;
             sm.pop_turn = r + 1;
           }
@@ -912,6 +950,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           if (lane == 0) {
             *reinterpret_cast<uint4*>(sm.rec_hdr[rs]) =
                 make_uint4((uint32_t)e, (uint32_t)cell, 0u, kDeadRecord);
+            __threadfence_block();
             rtags[rs] = (uint32_t)r;
           }
           continue;
@@ -960,7 +999,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
               (uint32_t)e, (uint32_t)cell | ((tag & 0xffu) << 16),
               (uint32_t)n_cand | ((uint32_t)min(n_cont, 0xffff) << 16), (uint32_t)seen);
         __syncwarp();
-        if (lane == 0) rtags[rs] = (uint32_t)r;
+        if (lane == 0) {
+          __threadfence_block();
+          rtags[rs] = (uint32_t)r;
+        }
       }
     } else if (warp < kProducers) {
       // ---- producers: entries 2p, 2p+1 (mod 2 * kProducers), two rows in flight ----------
@@ -991,16 +1033,40 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         uint32_t c0 = 0, c1 = 0;
         if (alive0) c0 = __ldg(tmem + cell0);
         if (alive1) c1 = __ldg(tmem + cell1);
-        if (alive0)
-          score_row<MODE>(tp + (cell0 >> 8) * 128, table, c0, is_aux, lane,
-                          sm.ring_row[e0 % kRing]);
-        if (alive1)
-          score_row<MODE>(tp + (cell1 >> 8) * 128, table, c1, is_aux, lane,
-                          sm.ring_row[e1 % kRing]);
-        __syncwarp();
-        if (lane == 0) {   // after __syncwarp: every lane's row stores are ordered before this
-          if (alive0) tags[e0 % kRing] = ((uint32_t)e0 << 8) | c0;
-          if (alive1) tags[e1 % kRing] = ((uint32_t)e1 << 8) | c1;
+        // Rows are scored into registers first and then stored under the slot's lock.  A
+        // producer can fall a whole ring revolution behind on an entry that died after
+        // its aliveness check (nobody waits for such a row, so the window moves on): the
+        // claim word keeps it from overwriting the row of the newer entry that owns the
+        // slot by then.
+        uint4 row0 = make_uint4(0, 0, 0, 0), row1 = row0;
+        if (alive0) row0 = score_row_regs<MODE>(tp + (cell0 >> 8) * 128, table, c0, is_aux, lane);
+        if (alive1) row1 = score_row_regs<MODE>(tp + (cell1 >> 8) * 128, table, c1, is_aux, lane);
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          const bool alive = which ? alive1 : alive0;
+          if (!alive) continue;
+          const int e = which ? e1 : e0;
+          const int slot = e % kRing;
+          if (lane == 0)
+            while (atomicCAS(&sm.ring_lock[slot], 0u, 1u) != 0u) {}
+          __syncwarp();
+          const bool mine =
+              reinterpret_cast<volatile uint32_t*>(sm.ring_claim)[slot] <= (uint32_t)e;
+          if (mine) {
+            reinterpret_cast<uint4*>(sm.ring_row[slot])[lane] = which ? row1 : row0;
+            __syncwarp();
+            if (lane == 0) {
+              // after __syncwarp: every lane's row stores are ordered before the tag
+              reinterpret_cast<volatile uint32_t*>(sm.ring_claim)[slot] = (uint32_t)e + 1u;
+              __threadfence_block();
+              tags[slot] = ((uint32_t)e << 8) | (which ? c1 : c0);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) {
+            __threadfence_block();
+            atomicExch(&sm.ring_lock[slot], 0u);
+          }
         }
       }
     } else if (warp == kApplyWarp) {
@@ -1030,7 +1096,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           const uint32_t group = __match_any_sync(kFull, mine ? page : 64 + lane);
           uint32_t pending = group;
           while (__any_sync(kFull, mine && pending != 0)) {
-            if (mine && pending != 0 && (pending & ((1u << lane) - 1u)) == 0) {
+            if (mine && pending != 0 && __ffs(pending) - 1 == lane) {   // my turn in my group
               apply_store<MODE>(sm.src, g_mem, page, off, is_aux, content);
               if (o1 != off) apply_store<MODE>(sm.src, g_mem, page, o1, is_aux, content);
               if (o2 != off) apply_store<MODE>(sm.src, g_mem, page, o2, is_aux, content);
