@@ -74,7 +74,6 @@ struct Smem {
   // consumer's own (re-queued cells are scored on demand).
   alignas(16) uint16_t ring_row[kRing + 1][256];
   uint32_t ring_tag[kRing];       // sorted-array index the slot holds
-  uint32_t ring_lock[kRing];      // a producer is writing the slot
   uint32_t ring_claim[kRing];     // 1 + newest entry that has written (or is writing) the slot
   // top byte of the tempered words of stream P (= getrandbits(8), video.py:178, :291):
   // slot s < 3 holds the block whose number is s (mod 3), slot 3 repeats slot 0, so that
@@ -596,7 +595,6 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     constexpr uint32_t kEndOfHeap = 0xffffffffu, kDeadRecord = 0xffffffffu;
     if (t < kRing) {
       sm.ring_tag[t] = 0xffffffffu;
-      sm.ring_lock[t] = 0;
       sm.ring_claim[t] = 0;
     }
     if (t < kRecRing) sm.rec_tag[t] = 0xffffffffu;
@@ -864,8 +862,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           rec.y |= (uint32_t)((emitted + 1) & 255) << 24;
           reinterpret_cast<volatile unsigned long long*>(sm.opq)[emitted % kOpQueue] =
               ((unsigned long long)rec.y << 32) | rec.x;
-          // the priorities above are in place: later front-end reads see this opcode
-          __threadfence_block();
+          // the priorities above are in place: later front-end reads see this opcode.  One
+          // thread's shared-memory stores are performed in program order; the barrier only
+          // keeps the compiler from sinking the plain stores below the volatile one.
+          asm volatile("" ::: "memory");
           if (!heap_done) sm.b_done = r;
         }
         n_pushed += push1 + push2;
@@ -1033,11 +1033,14 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         uint32_t c0 = 0, c1 = 0;
         if (alive0) c0 = __ldg(tmem + cell0);
         if (alive1) c1 = __ldg(tmem + cell1);
-        // Rows are scored into registers first and then stored under the slot's lock.  A
-        // producer can fall a whole ring revolution behind on an entry that died after
-        // its aliveness check (nobody waits for such a row, so the window moves on): the
-        // claim word keeps it from overwriting the row of the newer entry that owns the
-        // slot by then.
+        // Rows are scored into registers first and stored only while the entry is still
+        // inside the ring window.  A producer can fall a whole ring revolution behind on an
+        // entry that died after its aliveness check (nobody waits for such a row, so the
+        // window moves on); the slot may then already belong to entry e + kRing.  Guards:
+        // (1) the window check -- the newer entry's producer cannot even start scoring
+        // (two dependent global loads) before head has passed e, so a store issued right
+        // after seeing head <= e lands first; (2) the claim word, which keeps a row that is
+        // already newer from being replaced.
         uint4 row0 = make_uint4(0, 0, 0, 0), row1 = row0;
         if (alive0) row0 = score_row_regs<MODE>(tp + (cell0 >> 8) * 128, table, c0, is_aux, lane);
         if (alive1) row1 = score_row_regs<MODE>(tp + (cell1 >> 8) * 128, table, c1, is_aux, lane);
@@ -1047,10 +1050,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           if (!alive) continue;
           const int e = which ? e1 : e0;
           const int slot = e % kRing;
-          if (lane == 0)
-            while (atomicCAS(&sm.ring_lock[slot], 0u, 1u) != 0u) {}
-          __syncwarp();
           const bool mine =
+              sm.head <= e &&
               reinterpret_cast<volatile uint32_t*>(sm.ring_claim)[slot] <= (uint32_t)e;
           if (mine) {
             reinterpret_cast<uint4*>(sm.ring_row[slot])[lane] = which ? row1 : row0;
@@ -1058,15 +1059,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             if (lane == 0) {
               // after __syncwarp: every lane's row stores are ordered before the tag
               reinterpret_cast<volatile uint32_t*>(sm.ring_claim)[slot] = (uint32_t)e + 1u;
-              __threadfence_block();
               tags[slot] = ((uint32_t)e << 8) | (which ? c1 : c0);
             }
           }
           __syncwarp();
-          if (lane == 0) {
-            __threadfence_block();
-            atomicExch(&sm.ring_lock[slot], 0u);
-          }
         }
       }
     } else if (warp == kApplyWarp) {
