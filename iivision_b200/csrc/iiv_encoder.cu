@@ -2,12 +2,14 @@
 // (Video.encode_frame :72-93, _index_changes :95-251, _heapify_priorities
 //  :253-271, _compute_error :275-301) -- one thread block per clip.
 //
-// The opcode loop is a sequential dependency chain (each opcode mutates the
-// source bitmap and the priorities the next pop reads), so one clip cannot use
-// more than one block; the chip is filled by batching independent clips.  Inside
-// a block the work per opcode is data parallel over the 256 offsets of a page:
-// one table gather per thread, ballot/popc ranks for the RNG draws and
-// warp-REDUX min reductions for candidate selection.
+// The opcode loop is a sequential dependency chain (each opcode's nonces start where the
+// previous one's ended, and its stores change the priorities the next pop reads), so
+// one clip cannot use more than one block; the chip is filled by batching independent
+// clips.  Inside a block the segment runs in two phases: phase A (all 256 threads)
+// scores the bank, draws the heap nonces, radix-selects the reachable prefix of the
+// heap and sorts it; phase B cuts the loop into stages run by specialised warps --
+// row producers, speculative front ends, one decision warp, an applier and an MT19937
+// twister -- that talk through flag-guarded rings in shared memory (see phase B below).
 //
 // Exactness notes:
 //  * heapq pops the smallest (-priority, nonce, page, offset) tuple; with unique

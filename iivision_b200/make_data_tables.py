@@ -141,10 +141,32 @@ def compute_edit_distance(edp: EditDistanceParams, bitmap_cls: Type[screen.Bitma
     ``nominal_colours`` only validated pixel values upstream and is ignored.
     """
     table = compute_edit_distance_device(edp, bitmap_cls, ops.LAYOUT_TRIANGULAR)
-    host = torch.empty(table.shape, dtype=torch.uint16, pin_memory=True)
+    host = _pinned_result(tuple(table.shape))
     host.copy_(table, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return host.numpy()
+    return host.numpy()      # the array keeps `host` alive; see _pinned_result
+
+
+_pinned_pool = []
+
+
+def _pinned_result(shape) -> torch.Tensor:
+    """Page-locked uint16 buffer for a table on its way to the host.  cudaHostAlloc of
+    1 GiB costs tens of milliseconds, more than the copy itself, so buffers are kept and
+    handed out again once the array returned to the caller has been dropped: a live numpy
+    view (or anything derived from it) holds a reference to the tensor's storage."""
+    try:
+        use_count = torch._C._storage_Use_Count
+    except AttributeError:       # no way to tell whether a buffer is still in use
+        return torch.empty(shape, dtype=torch.uint16, pin_memory=True)
+    for t in _pinned_pool:
+        # 2 = the pooled tensor itself + the temporary storage object made for the query
+        if tuple(t.shape) == shape and use_count(t.untyped_storage()._cdata) <= 2:
+            return t
+    t = torch.empty(shape, dtype=torch.uint16, pin_memory=True)
+    if len(_pinned_pool) < 4:
+        _pinned_pool.append(t)
+    return t
 
 
 def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,

@@ -224,3 +224,20 @@ def test_static_helpers_against_reference_fixture(mods):
     assert s.HGRBitmap._double_pixels(0b1010101) == 0b111001100110011
     with pytest.raises(Exception):
         s.DHGRBitmap._part(3, np.uint64(1))
+
+
+def test_compute_edit_distance_results_do_not_alias(mods, oracle_luts):
+    """The pinned staging buffers are recycled only after the caller dropped the array."""
+    edp = mods.mdt.compute_substitute_costs(mods.palette.NTSCPalette)
+    a = mods.mdt.compute_edit_distance(edp, mods.screen.DHGRBitmap)
+    keep = a[0, 5000:5010].copy()
+    view = a[1]                                   # a derived view keeps the buffer busy
+    edp2 = mods.mdt.compute_substitute_costs(mods.palette.IIGSPalette)
+    b = mods.mdt.compute_edit_distance(edp2, mods.screen.DHGRBitmap)
+    assert not np.shares_memory(a, b)
+    assert np.array_equal(a[0, 5000:5010], keep) and not np.array_equal(a, b)
+    ptr = a.ctypes.data
+    del a, view
+    c = mods.mdt.compute_edit_distance(edp, mods.screen.DHGRBitmap)
+    assert c.ctypes.data == ptr                   # recycled now
+    assert np.array_equal(c[0, 5000:5010], keep)
