@@ -65,6 +65,10 @@ PROTOTYPES = {
                                  c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     "iiv_mt_draw": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "iiv_stream_length": (c_size_t, [c_size_t, c_int]),
+    "iiv_stream_ticks_within": (c_size_t, [c_size_t, c_size_t]),
+    "iiv_emit_stream": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_u32,
+                                c_u32, c_void_p, c_size_t, c_void_p, c_void_p]),
     "iiv_string_distance": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int,
                                     c_void_p, c_void_p]),
 }

@@ -229,6 +229,26 @@ int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
                      const uint16_t* d_table, uint8_t* d_opcodes,
                      int64_t* d_seg_info, void* stream);
 
+/* ---- next row N2: player byte stream (movie.py, opcodes.py) --------------------- */
+
+/* Movie.emit_stream (movie.py:122-161) with Machine.emit (machine.py:11-25) and the
+ * opcodes' emit_command / emit_data (opcodes.py:49-52, 79-89, 116-121, 144-146) for
+ * a Header followed by n_ticks tick opcodes, the Acks that close every 2 KiB frame
+ * (flipping MAIN/AUX in DHGR), Terminate and the zero padding.
+ *   d_opcodes   uint8[n_ticks][8] as written by iiv_encode_clips
+ *   d_ticks     uint8[n_ticks]    speaker duty-cycle ticks, 4..66 even (movie.py:104-107)
+ *   d_tick_addr uint16[32][32]    op_tick_<4+2i>_page_<32+j> start addresses
+ *                                 (opcodes.py:190-217, from player/iivision.dbg)
+ *   d_bad       int, set to 1 if a tick or page has no opcode
+ * iiv_stream_length gives the byte count (multiple of 2048); iiv_stream_ticks_within
+ * the number of ticks Movie.emit_stream emits before max_bytes_out stops it (:133). */
+size_t iiv_stream_length(size_t n_ticks, int with_header);
+size_t iiv_stream_ticks_within(size_t n_ticks, size_t max_bytes_out);
+int iiv_emit_stream(int mode, const uint8_t* d_opcodes, const uint8_t* d_ticks,
+                    size_t n_ticks, const uint16_t* d_tick_addr, uint32_t ack_addr,
+                    uint32_t terminate_addr, uint8_t* d_out, size_t out_capacity,
+                    int* d_bad, void* stream);
+
 /* MT19937 helpers used by the Python facade to keep the process-global
  * generators in step (device-side draws, host-visible state). */
 int iiv_mt_draw(uint32_t* d_mt625, uint32_t* d_words, int n, void* stream);

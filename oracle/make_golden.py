@@ -19,6 +19,8 @@ The reference cannot travel to the GPU box, so its outputs do, as fixtures:
                        encoder state and the next words of both RNG streams
   helpers.npz          _make_header, _make_footer, _body, _fix_column_left/right and
                        _double_pixels outputs of the reference classes
+  byte_stream.npz      Movie.emit_stream bytes for synthetic tick opcodes + the opcode
+                       address table of player/iivision.dbg
   luts.json            int(dE2000) substitution matrices from oracle/cie2000.py
                        (restated colormath; NOT reference output -- the reference
                        generator cannot run offline) together with the rows
@@ -179,6 +181,43 @@ def gen_helpers(ns):
     np.savez_compressed(os.path.join(GOLDEN, "helpers.npz"), **out)
 
 
+def gen_byte_stream(ns):
+    """Movie.emit_stream (movie.py:122-161) over synthetic tick opcodes, and the player's
+    opcode address table parsed from player/iivision.dbg (opcodes.py:170-217)."""
+    out = {}
+    tick_addr = np.zeros((32, 32), np.uint16)
+    for i, tick in enumerate(range(4, 68, 2)):
+        for j, page in enumerate(range(32, 64)):
+            tick_addr[i, j] = ns.opcodes.TICK_OPCODES[(tick, page)]._START
+    out["tick_addr"] = tick_addr
+    out["ack_addr"] = np.uint32(ns.opcodes.Ack._START)
+    out["terminate_addr"] = np.uint32(ns.opcodes.Terminate._START)
+    rng = np.random.default_rng(41)
+    for mode in ("HGR", "DHGR"):
+        vm = getattr(ns.video_mode.VideoMode, mode)
+        for name, n, max_out in (("short", 5, None), ("frames", 900, None),
+                                 ("exact", 291 + 292, None), ("capped", 2000, 5000)):
+            pages = rng.integers(32, 64, size=n)
+            ticks = rng.integers(2, 34, size=n) * 2
+            content = rng.integers(0, 256 if mode == "HGR" else 128, size=n)
+            offs = rng.integers(0, 256, size=(n, 4))
+            m = ns.movie.Movie.__new__(ns.movie.Movie)
+            m.video_mode, m.max_bytes_out, m.stream_pos = vm, max_out, 0
+            m.state, m.aux_memory_bank = ns.machine.Machine(), False
+            ops = [ns.opcodes.Header(mode=vm)] + [
+                ns.opcodes.TICK_OPCODES[(int(ticks[k]), int(pages[k]))](
+                    int(content[k]), tuple(int(x) for x in offs[k])) for k in range(n)]
+            data = bytes(m.emit_stream(ops))
+            rec = np.zeros((n, 8), np.uint8)
+            rec[:, 0], rec[:, 1], rec[:, 2:6], rec[:, 6] = pages, content, offs, 1
+            key = "%s_%s" % (mode.lower(), name)
+            out[key + "_records"] = rec
+            out[key + "_ticks"] = ticks.astype(np.uint8)
+            out[key + "_max"] = np.int64(max_out or 0)
+            out[key + "_bytes"] = np.frombuffer(data, np.uint8)
+    np.savez_compressed(os.path.join(GOLDEN, "byte_stream.npz"), **out)
+
+
 def gen_stream(ns, case, table):
     name, mode, n_frames, fraction, fseed, seed, per_frame, flip = case
     ref_harness.install_tables(ns, mode, {5: table})
@@ -244,6 +283,7 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ns = ref_harness.load()
     print("helpers"); gen_helpers(ns)
+    print("byte stream"); gen_byte_stream(ns)
     if "--helpers-only" in sys.argv:
         return
     print("pixel strings"); gen_pixel_strings(ns)

@@ -9,8 +9,9 @@ committed fixtures under ``tests/golden/`` (see ``oracle/make_golden.py``).
 What can be imported: screen.py, colours.py, palette.py, video.py, opcodes.py,
 machine.py, symbol_table.py, video_mode.py, frame_grabber.py -- given
   * ``np.bool8`` alias (reference screen.py:42 uses the numpy<2 name),
-  * stub ``colormath.color_objects`` (palette.py:6-15) and ``skvideo.io``
-    (frame_grabber.py:10) from ``oracle/ref_shims``,
+  * stub ``colormath.color_objects`` (palette.py:6-15), ``skvideo.io``
+    (frame_grabber.py:10), ``audioread`` and ``librosa`` (audio.py:5-6, only imported)
+    from ``oracle/ref_shims``,
   * CWD containing ``player/iivision.dbg`` while opcodes.py is imported
     (opcodes.py:173 opens it by relative path at import time).
 What cannot: make_data_tables.py (needs colormath 3.0.0, weighted-levenshtein
@@ -27,7 +28,7 @@ REFERENCE_ROOT = os.environ.get("IIV_REFERENCE_ROOT", "/root/reference")
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
 _MODULES = (
     "colours", "palette", "video_mode", "symbol_table", "machine", "opcodes",
-    "screen", "frame_grabber", "video",
+    "screen", "frame_grabber", "video", "audio", "movie",
 )
 _cache = None
 

@@ -241,3 +241,28 @@ def test_compute_edit_distance_results_do_not_alias(mods, oracle_luts):
     c = mods.mdt.compute_edit_distance(edp, mods.screen.DHGRBitmap)
     assert c.ctypes.data == ptr                   # recycled now
     assert np.array_equal(c[0, 5000:5010], keep)
+
+
+@pytest.mark.parametrize("mode", ["HGR", "DHGR"])
+def test_emit_stream_device_matches_reference_bytes(mode):
+    """iiv_emit_stream against bytes produced by the reference's Movie.emit_stream."""
+    import torch
+    from iivision_b200 import movie
+    g = np.load(os.path.join(GOLDEN, "byte_stream.npz"))
+    addresses = (g["tick_addr"], int(g["ack_addr"]), int(g["terminate_addr"]))
+    for case in ("short", "frames", "exact", "capped"):
+        key = "%s_%s" % (mode.lower(), case)
+        rec = torch.from_numpy(g[key + "_records"]).cuda()
+        ticks = torch.from_numpy(g[key + "_ticks"]).cuda()
+        out = movie.emit_stream_device(mode, rec, ticks, int(g[key + "_max"]) or None, addresses)
+        assert np.array_equal(out.cpu().numpy(), g[key + "_bytes"]), key
+    empty = movie.emit_stream_device(mode, torch.zeros((0, 8), dtype=torch.uint8, device="cuda"),
+                                     torch.zeros((0,), dtype=torch.uint8, device="cuda"),
+                                     None, addresses).cpu().numpy()
+    assert len(empty) == 2048 and empty[6] == (1 if mode == "DHGR" else 0)
+    assert (empty[7] << 8 | empty[8]) == int(g["terminate_addr"])
+    bad = torch.from_numpy(g["hgr_short_ticks"].copy()).cuda()
+    bad[2] = 5
+    with pytest.raises(KeyError):
+        movie.emit_stream_device(mode, torch.from_numpy(g["hgr_short_records"]).cuda(), bad,
+                                 None, addresses)
