@@ -260,7 +260,7 @@ def test_emit_stream_device_matches_reference_bytes(mode):
                                      torch.zeros((0,), dtype=torch.uint8, device="cuda"),
                                      None, addresses).cpu().numpy()
     assert len(empty) == 2048 and empty[6] == (1 if mode == "DHGR" else 0)
-    assert (empty[7] << 8 | empty[8]) == int(g["terminate_addr"])
+    assert (int(empty[7]) << 8 | int(empty[8])) == int(g["terminate_addr"])
     bad = torch.from_numpy(g["hgr_short_ticks"].copy()).cuda()
     bad[2] = 5
     with pytest.raises(KeyError):
