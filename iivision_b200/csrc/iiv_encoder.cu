@@ -1245,7 +1245,7 @@ extern "C" int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
   IIV_REQUIRE(mode == IIV_MODE_HGR || mode == IIV_MODE_DHGR, "bad mode %d", mode);
   IIV_REQUIRE(n_clips >= 0 && n_frames > 0 && n_segments >= 0, "bad counts");
   IIV_REQUIRE(d_state && d_target_mem && d_target_packed && h_segments && d_table &&
-                  d_opcodes && d_seg_info, "null pointer");
+                  d_seg_info, "null pointer");
   IIV_REQUIRE(state_stride >= kStateBytes && state_stride % 16 == 0,
               "state_stride %zu too small or unaligned", state_stride);
   if (n_clips == 0 || n_segments == 0) return 0;
@@ -1257,6 +1257,7 @@ extern "C" int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
     IIV_REQUIRE(q[2] >= 0 && q[2] <= kMaxBudget, "segment %d: budget %d outside 0..%d", s, q[2], kMaxBudget);
     total += q[2];
   }
+  IIV_REQUIRE(d_opcodes || total == 0, "null opcode buffer");
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* d_segments = nullptr;
   IIV_CUDA(cudaMallocAsync(&d_segments, sizeof(int32_t) * 3 * n_segments, st));
