@@ -352,6 +352,24 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    exchange_note = None
+    if world > 1 and exchange != "nccl":
+        # symmetric (peer-mapped) memory needs NVLink P2P between all ranks; if the
+        # rendezvous fails on this box every rank falls back to the NCCL all-gather
+        ok = 1
+        try:
+            sharded_step(exchange)
+            torch.cuda.synchronize()
+        except Exception as e:   # noqa: BLE001
+            ok = 0
+            exchange_note = "fused exchange unavailable (%s); NCCL all-gather used" % (
+                str(e).splitlines()[0][:120])
+        flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            exchange = "nccl"
+            exchange_note = exchange_note or "fused exchange unavailable on another rank"
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.3 if rank == 0 else 0)
     # warm-up: at least W (>= 3) steps AND >= 1.2 s of back-to-back generator
@@ -398,8 +416,8 @@ def run_ours(args, rank, world, local_rank):
             try:
                 for _ in range(3):
                     sharded_step(other)
-            except RuntimeError as e:       # e.g. no multicast on this fabric
-                alt.append({"exchange": other, "unavailable": str(e)[:80]})
+            except Exception as e:          # e.g. no multicast on this fabric  # noqa: BLE001
+                alt.append({"exchange": other, "unavailable": str(e).splitlines()[0][:80]})
                 continue
             barrier()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -504,7 +522,8 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic (palette constants; no external data)",
-        "config": workload_config(world, exchange),
+        "config": dict(workload_config(world, exchange),
+                       **({"exchange_note": exchange_note} if exchange_note else {})),
         "clocks": clocks,
         "e2e": {"value": ENTRIES * e2e_steps / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": 16 * 3 + 256 * 4,
