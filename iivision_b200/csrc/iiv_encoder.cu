@@ -189,6 +189,7 @@ __device__ __forceinline__ void fill_nonces(const uint32_t* __restrict__ block, 
 // (Bitmap._diff_weights_page with source = target, screen.py:453-494, 544): lane l
 // owns offsets 8l .. 8l+7, i.e. packed columns 4l .. 4l+3.  Screen holes (lanes 15
 // and 31) get 0xffff so that they are never candidates.
+// (the lane's 8 values are returned packed as 16-bit pairs)
 template <int MODE>
 __device__ __forceinline__ uint4 score_row_regs(const uint64_t* __restrict__ tp_row,
                                                 const uint16_t* __restrict__ table,
@@ -221,27 +222,8 @@ __device__ __forceinline__ void score_row(const uint64_t* __restrict__ tp_row,
                                           const uint16_t* __restrict__ table,
                                           uint32_t content, int is_aux, int lane,
                                           uint16_t* __restrict__ out_row) {
-  using M = Mode<MODE>;
-  uint4 packed_out = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-  if ((lane & 15) != 15) {
-    const ulonglong2 w01 = __ldg(reinterpret_cast<const ulonglong2*>(tp_row) + 2 * lane);
-    const ulonglong2 w23 = __ldg(reinterpret_cast<const ulonglong2*>(tp_row) + 2 * lane + 1);
-    const uint64_t w[4] = {w01.x, w01.y, w23.x, w23.y};
-    uint32_t nd[8];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int o = byte_offset<MODE>(half, is_aux);
-        const uint32_t x = mask_shift<MODE>(masked_update<MODE>(o, w[q], content), o);
-        const uint32_t y = mask_shift<MODE>(w[q], o);
-        nd[2 * q + half] =
-            __ldg(table + ((size_t)o << (2 * M::kBits)) + ((size_t)x << M::kBits) + y);
-      }
-    packed_out = make_uint4(nd[0] | (nd[1] << 16), nd[2] | (nd[3] << 16),
-                            nd[4] | (nd[5] << 16), nd[6] | (nd[7] << 16));
-  }
-  reinterpret_cast<uint4*>(out_row)[lane] = packed_out;
+  reinterpret_cast<uint4*>(out_row)[lane] =
+      score_row_regs<MODE>(tp_row, table, content, is_aux, lane);
 }
 
 __device__ __forceinline__ uint64_t first_pass_key(int32_t prio, uint32_t nonce,
