@@ -213,6 +213,16 @@ class ClockSampler:
 
 # ---- our arm ----------------------------------------------------------------------------------
 
+def ncu_traffic():
+    """DRAM bytes per launch of the generator from the committed ncu capture (N = 1,
+    whole HGR table), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "tree_kernel_traffic.json")) as f:
+            return float(json.load(f)["traffic_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -541,7 +551,8 @@ def run_ours(args, rank, world, local_rank):
                         "per-rank row block generate + D2H of that block"},
         "gpu_launches": ops.launches_per_table_generate() * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": ncu_traffic() if world == 1 else None,
                      "peak_source": peak_src, "kernel": ops.generator_kernel_name(),
                      "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,
