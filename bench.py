@@ -447,6 +447,21 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             alt.append({"exchange": other, "ms_per_step": float(t.item()) / args.steps,
                         "value": ENTRIES * args.steps / (float(t.item()) * 1e-3)})
+        # and no exchange at all: every rank generates the whole table for itself.  One GPU
+        # makes the table faster than NVLink can deliver (N-1)/N of it, so this is the
+        # quickest way to have it on every GPU; listed for reference, not the headline.
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(args.steps):
+            ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
+        a1.record(stream)
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        alt.append({"exchange": "none (replicated: each rank generates all rows)",
+                    "ms_per_step": float(t.item()) / args.steps,
+                    "value": ENTRIES * args.steps / (float(t.item()) * 1e-3)})
 
     # kernel-only timing for the roofline: the generator kernel(s) of this rank's rows
     rows = parallel.row_partition(1 << BITS, world)[rank]
