@@ -315,12 +315,19 @@ def scorer_figures(torch, ops, single=True):
         return times[len(times) // 2], times, trace
 
     n_clips, n_frames = int(os.environ.get("IIV_BENCH_CLIPS", "148")), 4
-    ms, all_ms, trace = encode_run(n_clips, n_frames)
+    sampler = ClockSampler(torch.cuda.current_device())
+    time.sleep(0.3)
+    t_enc0 = time.perf_counter()
+    ms, all_ms, trace = encode_run(n_clips, n_frames, reps=25)
     out["encoded_trace_clip0"] = trace
     out["encoded_frames_per_s"] = n_clips * n_frames / (ms * 1e-3)
     out["encoded_note"] = ("%d independent DHGR clips x %d frames, one block per clip; median "
-                           "of %d runs (ms: %s)" % (n_clips, n_frames, len(all_ms),
-                                                    ", ".join("%.2f" % x for x in all_ms)))
+                           "of %d runs (ms min/median/max: %.2f / %.2f / %.2f)" % (
+                               n_clips, n_frames, len(all_ms), all_ms[0], ms, all_ms[-1]))
+    out["encoded_clocks"] = sampler.summary(t_enc0, time.perf_counter())
+    sampler.stop()
+    sm_mhz = out["encoded_clocks"].get("sm_mhz") or 1965.0
+    out["encoded_ms_from_sm_cycles"] = trace["slowest_clip_sm_cycles"] / (sm_mhz * 1e3)
     if not single:
         return out
     ms1, all1, trace1 = encode_run(1, 16)
