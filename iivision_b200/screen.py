@@ -124,7 +124,7 @@ class MemoryMap:
 # ---- host <-> device staging ------------------------------------------------------
 
 def _h2d_u64(a) -> torch.Tensor:
-    a = np.ascontiguousarray(a, dtype=np.uint64)
+    a = np.require(a, dtype=np.uint64, requirements=["C", "W"])   # copies read-only input
     return torch.from_numpy(a.view(np.int64)).cuda()
 
 
@@ -133,7 +133,7 @@ def _d2h_u64(t: torch.Tensor) -> np.ndarray:
 
 
 def _h2d_u8(a) -> torch.Tensor:
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8)).cuda()
+    return torch.from_numpy(np.require(a, dtype=np.uint8, requirements=["C", "W"])).cuda()
 
 
 class Bitmap:
