@@ -330,6 +330,14 @@ def scorer_figures(torch, ops, single=True):
     out["encoded_ms_from_sm_cycles"] = trace["slowest_clip_sm_cycles"] / (sm_mhz * 1e3)
     if not single:
         return out
+    # BASELINE.json configs[0]: HGR NTSC, one 60-frame 280x192 clip (980 opcodes per frame,
+    # a single bank), next to the reference's algorithm on the host: oracle/scorer.py keeps
+    # the reference's cost structure (whole-array numpy calls per opcode, heapq, Python RNG
+    # draws; one core, like the reference)
+    try:
+        out.update(hgr_clip_and_cpu(torch, ops, table_dhgr=table))
+    except Exception as e:   # noqa: BLE001
+        out["hgr_clip_error"] = repr(e)
     ms1, all1, trace1 = encode_run(1, 16)
     out["single_clip_trace"] = trace1
     out["single_clip_frames_per_s"] = 16 / (ms1 * 1e-3)
@@ -337,6 +345,70 @@ def scorer_figures(torch, ops, single=True):
     out["single_clip_note"] = ("one DHGR clip of 16 frames (980 opcodes/frame, bank flip every "
                                "292) on one SM; median of %d runs (ms: %s)" % (
                                    len(all1), ", ".join("%.2f" % x for x in all1)))
+    return out
+
+
+def hgr_clip_and_cpu(torch, ops, table_dhgr):
+    import random
+    import numpy as np
+    from iivision_b200 import palette, synth
+    from oracle import scorer
+    out = {}
+    lut = ops.lut_cie2000(palette.NTSCPalette.rgb_by_value())
+    table = ops.table_generate("HGR", lut, layout=ops.LAYOUT_SYMMETRIC)
+    n_frames = 60
+    frames = synth.synthetic_frames("HGR", n_frames, 1.0, seed=7)
+    segs = synth.movie_schedule("HGR", n_frames)
+    tmem = torch.from_numpy(np.ascontiguousarray(frames[None])).cuda()
+    tpacked = ops.pack("HGR", tmem[0, :, 0].contiguous()).view(1, n_frames, 32, 128)
+    pad = np.zeros(640, np.uint32)
+
+    def fresh():
+        st = ops.new_clip_states(1)
+        pad[:625] = ops.mt_from_python(random.Random(0).getstate())
+        ops.state_field(st, ops.F_MT_PY, torch.int32, (640,)).copy_(
+            torch.from_numpy(pad.view(np.int32)).cuda().expand(1, 640))
+        pad[:625] = ops.mt_from_numpy(np.random.RandomState(0).get_state())
+        ops.state_field(st, ops.F_MT_NP, torch.int32, (640,)).copy_(
+            torch.from_numpy(pad.view(np.int32)).cuda().expand(1, 640))
+        return st
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    opc = torch.empty((1, n_frames * 980, 8), dtype=torch.uint8, device="cuda")
+    info = torch.zeros((1, len(segs), 8), dtype=torch.int64, device="cuda")
+    times = []
+    for r in range(4):
+        st = fresh()
+        torch.cuda.synchronize()
+        ev[0].record()
+        ops.encode_clips("HGR", st, tmem, tpacked, segs, table, opcodes=opc, seg_info=info)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if r:
+            times.append(ev[0].elapsed_time(ev[1]))
+    times.sort()
+    out["hgr_60_frame_clip_frames_per_s"] = n_frames / (times[len(times) // 2] * 1e-3)
+    gpu_ops = opc.cpu().numpy()[0]
+    # the same clip's first frames through the CPU restatement of the reference's path
+    host_table = table.cpu().numpy()
+    cpu_frames = 3
+    v = scorer.OracleVideo("HGR", host_table, py_rng=random.Random(0),
+                           np_rng=np.random.RandomState(0))
+    t0 = time.perf_counter()
+    cpu_ops = []
+    for fr in range(cpu_frames):
+        seq = v.encode_frame(v.target_bitmap(frames[fr, 0]), False)
+        for _ in range(980):
+            page, content, offs = next(seq)
+            cpu_ops.append([page, content] + list(offs))
+    dt = time.perf_counter() - t0
+    out["hgr_cpu_port_frames_per_s"] = cpu_frames / dt
+    out["hgr_cpu_port_note"] = ("oracle/scorer.py (numpy + heapq restatement of screen.py / "
+                                "video.py, 1 core) on the first %d frames of the same clip: "
+                                "%.0f us per opcode; its opcodes equal the GPU's: %s" % (
+                                    cpu_frames, dt * 1e6 / (cpu_frames * 980),
+                                    bool(np.array_equal(np.array(cpu_ops, np.uint8),
+                                                        gpu_ops[:cpu_frames * 980, :6]))))
+    del table
     return out
 
 
