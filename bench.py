@@ -275,6 +275,7 @@ def scorer_figures(torch, ops, single=True):
                           for c in range(min(n_clips, 4))])
         clips = np.concatenate([clips] * (n_clips // clips.shape[0] + 1))[:n_clips]
         segs = synth.movie_schedule("DHGR", n_frames)
+        plan = ops.SegmentPlan(segs)      # schedule resident on the device: pure launches
         tmem = torch.from_numpy(np.ascontiguousarray(clips)).cuda()
         flat = tmem.view(-1, 2, 32, 256)
         tpacked = ops.pack("DHGR", flat[:, 0].contiguous(), flat[:, 1].contiguous()).view(
@@ -300,7 +301,7 @@ def scorer_figures(torch, ops, single=True):
             st = fresh_states()
             torch.cuda.synchronize()
             ev[0].record()
-            ops.encode_clips("DHGR", st, tmem, tpacked, segs, table, opcodes=opc, seg_info=info)
+            ops.encode_clips("DHGR", st, tmem, tpacked, plan, table, opcodes=opc, seg_info=info)
             ev[1].record()
             torch.cuda.synchronize()
             if r >= 2:
@@ -358,7 +359,7 @@ def hgr_clip_and_cpu(torch, ops, table_dhgr):
     table = ops.table_generate("HGR", lut, layout=ops.LAYOUT_SYMMETRIC)
     n_frames = 60
     frames = synth.synthetic_frames("HGR", n_frames, 1.0, seed=7)
-    segs = synth.movie_schedule("HGR", n_frames)
+    segs = ops.SegmentPlan(synth.movie_schedule("HGR", n_frames))
     tmem = torch.from_numpy(np.ascontiguousarray(frames[None])).cuda()
     tpacked = ops.pack("HGR", tmem[0, :, 0].contiguous()).view(1, n_frames, 32, 128)
     pad = np.zeros(640, np.uint32)

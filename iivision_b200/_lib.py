@@ -64,6 +64,9 @@ PROTOTYPES = {
     "iiv_encode_clips": (c_int, [c_int, c_int, c_void_p, c_size_t, c_void_p,
                                  c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    "iiv_encode_clips_planned": (c_int, [c_int, c_int, c_void_p, c_size_t, c_void_p,
+                                         c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "iiv_mt_draw": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "iiv_stream_length": (c_size_t, [c_size_t, c_int]),
     "iiv_stream_ticks_within": (c_size_t, [c_size_t, c_size_t]),

@@ -1218,19 +1218,8 @@ extern "C" int iiv_clip_state_layout(size_t* offsets8) {
   return 0;
 }
 
-extern "C" int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
-                                size_t state_stride, const uint8_t* d_target_mem,
-                                const uint64_t* d_target_packed, int n_frames,
-                                const int32_t* h_segments, int n_segments,
-                                const uint16_t* d_table, uint8_t* d_opcodes,
-                                int64_t* d_seg_info, void* stream) {
-  IIV_REQUIRE(mode == IIV_MODE_HGR || mode == IIV_MODE_DHGR, "bad mode %d", mode);
-  IIV_REQUIRE(n_clips >= 0 && n_frames > 0 && n_segments >= 0, "bad counts");
-  IIV_REQUIRE(d_state && d_target_mem && d_target_packed && h_segments && d_table &&
-                  d_seg_info, "null pointer");
-  IIV_REQUIRE(state_stride >= kStateBytes && state_stride % 16 == 0,
-              "state_stride %zu too small or unaligned", state_stride);
-  if (n_clips == 0 || n_segments == 0) return 0;
+static int check_segments(int mode, int n_frames, const int32_t* h_segments, int n_segments,
+                          int64_t* total_out) {
   int64_t total = 0;
   for (int s = 0; s < n_segments; ++s) {
     const int32_t* q = h_segments + 3 * s;
@@ -1239,34 +1228,97 @@ extern "C" int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
     IIV_REQUIRE(q[2] >= 0 && q[2] <= kMaxBudget, "segment %d: budget %d outside 0..%d", s, q[2], kMaxBudget);
     total += q[2];
   }
+  *total_out = total;
+  return 0;
+}
+
+static int launch_encode(int mode, int n_clips, uint8_t* d_state, size_t state_stride,
+                         const uint8_t* d_target_mem, const uint64_t* d_target_packed,
+                         int n_frames, const int32_t* d_segments, int n_segments, int64_t total,
+                         const uint16_t* d_table, uint8_t* d_opcodes, int64_t* d_seg_info,
+                         cudaStream_t st) {
+  const size_t smem = sizeof(Smem);
+  cudaError_t e;
+  if (mode == IIV_MODE_HGR) {
+    e = cudaFuncSetAttribute(encode_kernel<IIV_MODE_HGR>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      encode_kernel<IIV_MODE_HGR><<<n_clips, kThreads, smem, st>>>(
+          d_state, state_stride, d_target_mem, d_target_packed, n_frames, d_segments,
+          n_segments, d_table, d_opcodes, total, d_seg_info);
+  } else {
+    e = cudaFuncSetAttribute(encode_kernel<IIV_MODE_DHGR>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      encode_kernel<IIV_MODE_DHGR><<<n_clips, kThreads, smem, st>>>(
+          d_state, state_stride, d_target_mem, d_target_packed, n_frames, d_segments,
+          n_segments, d_table, d_opcodes, total, d_seg_info);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "encode_kernel");
+  return 0;
+}
+
+static int check_encode_args(int mode, int n_clips, const void* d_state, size_t state_stride,
+                             const void* d_target_mem, const void* d_target_packed,
+                             int n_frames, int n_segments, const void* d_table,
+                             const void* d_seg_info) {
+  IIV_REQUIRE(mode == IIV_MODE_HGR || mode == IIV_MODE_DHGR, "bad mode %d", mode);
+  IIV_REQUIRE(n_clips >= 0 && n_frames > 0 && n_segments >= 0, "bad counts");
+  IIV_REQUIRE(d_state && d_target_mem && d_target_packed && d_table && d_seg_info,
+              "null pointer");
+  IIV_REQUIRE(state_stride >= kStateBytes && state_stride % 16 == 0,
+              "state_stride %zu too small or unaligned", state_stride);
+  return 0;
+}
+
+extern "C" int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
+                                size_t state_stride, const uint8_t* d_target_mem,
+                                const uint64_t* d_target_packed, int n_frames,
+                                const int32_t* h_segments, int n_segments,
+                                const uint16_t* d_table, uint8_t* d_opcodes,
+                                int64_t* d_seg_info, void* stream) {
+  int rc = check_encode_args(mode, n_clips, d_state, state_stride, d_target_mem,
+                             d_target_packed, n_frames, n_segments, d_table, d_seg_info);
+  if (rc) return rc;
+  IIV_REQUIRE(h_segments || n_segments == 0, "null pointer");
+  if (n_clips == 0 || n_segments == 0) return 0;
+  int64_t total = 0;
+  rc = check_segments(mode, n_frames, h_segments, n_segments, &total);
+  if (rc) return rc;
   IIV_REQUIRE(d_opcodes || total == 0, "null opcode buffer");
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* d_segments = nullptr;
   IIV_CUDA(cudaMallocAsync(&d_segments, sizeof(int32_t) * 3 * n_segments, st));
   cudaError_t e = cudaMemcpyAsync(d_segments, h_segments, sizeof(int32_t) * 3 * n_segments,
                                   cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) {
-    const size_t smem = sizeof(Smem);
-    if (mode == IIV_MODE_HGR) {
-      e = cudaFuncSetAttribute(encode_kernel<IIV_MODE_HGR>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess)
-        encode_kernel<IIV_MODE_HGR><<<n_clips, kThreads, smem, st>>>(
-            d_state, state_stride, d_target_mem, d_target_packed, n_frames, d_segments,
-            n_segments, d_table, d_opcodes, total, d_seg_info);
-    } else {
-      e = cudaFuncSetAttribute(encode_kernel<IIV_MODE_DHGR>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess)
-        encode_kernel<IIV_MODE_DHGR><<<n_clips, kThreads, smem, st>>>(
-            d_state, state_stride, d_target_mem, d_target_packed, n_frames, d_segments,
-            n_segments, d_table, d_opcodes, total, d_seg_info);
-    }
-    if (e == cudaSuccess) e = cudaGetLastError();
-  }
+  if (e == cudaSuccess)
+    rc = launch_encode(mode, n_clips, d_state, state_stride, d_target_mem, d_target_packed,
+                       n_frames, d_segments, n_segments, total, d_table, d_opcodes,
+                       d_seg_info, st);
   cudaFreeAsync(d_segments, st);
-  if (e != cudaSuccess) return cuda_fail(e, "encode_kernel");
-  return 0;
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(segments)");
+  return rc;
+}
+
+extern "C" int iiv_encode_clips_planned(int mode, int n_clips, uint8_t* d_state,
+                                        size_t state_stride, const uint8_t* d_target_mem,
+                                        const uint64_t* d_target_packed, int n_frames,
+                                        const int32_t* h_segments, const int32_t* d_segments,
+                                        int n_segments, const uint16_t* d_table,
+                                        uint8_t* d_opcodes, int64_t* d_seg_info, void* stream) {
+  int rc = check_encode_args(mode, n_clips, d_state, state_stride, d_target_mem,
+                             d_target_packed, n_frames, n_segments, d_table, d_seg_info);
+  if (rc) return rc;
+  IIV_REQUIRE((h_segments && d_segments) || n_segments == 0, "null pointer");
+  if (n_clips == 0 || n_segments == 0) return 0;
+  int64_t total = 0;
+  rc = check_segments(mode, n_frames, h_segments, n_segments, &total);
+  if (rc) return rc;
+  IIV_REQUIRE(d_opcodes || total == 0, "null opcode buffer");
+  return launch_encode(mode, n_clips, d_state, state_stride, d_target_mem, d_target_packed,
+                       n_frames, d_segments, n_segments, total, d_table, d_opcodes, d_seg_info,
+                       (cudaStream_t)stream);
 }
 
 extern "C" int iiv_mt_draw(uint32_t* d_mt625, uint32_t* d_words, int n, void* stream) {

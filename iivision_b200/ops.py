@@ -346,6 +346,19 @@ def state_field(states: torch.Tensor, field: int, dtype, shape) -> torch.Tensor:
 F_PACKED, F_MAIN, F_AUX, F_PRIO_MAIN, F_PRIO_AUX, F_MT_NP, F_MT_PY, F_FLAGS = range(8)
 
 
+class SegmentPlan:
+    """A (frame, is_aux, budget) schedule kept on the device as well, for encode_clips
+    calls that repeat it: no allocation or host-to-device copy per call."""
+
+    def __init__(self, segments):
+        self.host = np.ascontiguousarray(segments, dtype=np.int32).reshape(-1, 3)
+        self.device = torch.from_numpy(self.host).cuda()
+        self.total = int(self.host[:, 2].sum())
+
+    def __len__(self):
+        return self.host.shape[0]
+
+
 def encode_clips(mode, states: torch.Tensor, target_mem: torch.Tensor,
                  target_packed: torch.Tensor, segments, table: torch.Tensor,
                  opcodes: torch.Tensor = None, seg_info: torch.Tensor = None):
@@ -355,7 +368,8 @@ def encode_clips(mode, states: torch.Tensor, target_mem: torch.Tensor,
     int64[n_clips, n_frames, 32, 128].  Returns (opcodes uint8[n_clips,
     total_budget, 8], seg_info int64[n_clips, n_segments, 8])."""
     m = mode_id(mode)
-    segs = np.ascontiguousarray(segments, dtype=np.int32).reshape(-1, 3)
+    plan = segments if isinstance(segments, SegmentPlan) else None
+    segs = plan.host if plan else np.ascontiguousarray(segments, dtype=np.int32).reshape(-1, 3)
     n_clips, n_frames = target_mem.shape[0], target_mem.shape[1]
     banks = 2 if m == MODE_DHGR else 1
     if target_mem.shape != (n_clips, n_frames, banks, 32, 256):
@@ -370,10 +384,16 @@ def encode_clips(mode, states: torch.Tensor, target_mem: torch.Tensor,
     if seg_info is None:
         seg_info = torch.zeros((n_clips, segs.shape[0], 8), dtype=torch.int64,
                                device="cuda")
-    check(lib.iiv_encode_clips(
-        m, n_clips, _ptr(states), STATE_BYTES, _ptr(target_mem),
-        _ptr(target_packed), n_frames, segs.ctypes.data, segs.shape[0],
-        _ptr(table), _ptr(opcodes), _ptr(seg_info), _stream()))
+    if plan is not None:
+        check(lib.iiv_encode_clips_planned(
+            m, n_clips, _ptr(states), STATE_BYTES, _ptr(target_mem), _ptr(target_packed),
+            n_frames, segs.ctypes.data, _ptr(plan.device), segs.shape[0], _ptr(table),
+            opcodes.data_ptr() or None, _ptr(seg_info), _stream()))
+    else:
+        check(lib.iiv_encode_clips(
+            m, n_clips, _ptr(states), STATE_BYTES, _ptr(target_mem),
+            _ptr(target_packed), n_frames, segs.ctypes.data, segs.shape[0],
+            _ptr(table), opcodes.data_ptr() or None, _ptr(seg_info), _stream()))
     return opcodes, seg_info
 
 

@@ -229,6 +229,16 @@ int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
                      const uint16_t* d_table, uint8_t* d_opcodes,
                      int64_t* d_seg_info, void* stream);
 
+/* Same, for a schedule that is run more than once: the caller keeps a device copy of the
+ * segments (d_segments, same contents as h_segments) so the call is a pure kernel launch
+ * -- no allocation, no host-to-device copy on the stream.  h_segments is only validated. */
+int iiv_encode_clips_planned(int mode, int n_clips, uint8_t* d_state,
+                             size_t state_stride, const uint8_t* d_target_mem,
+                             const uint64_t* d_target_packed, int n_frames,
+                             const int32_t* h_segments, const int32_t* d_segments,
+                             int n_segments, const uint16_t* d_table, uint8_t* d_opcodes,
+                             int64_t* d_seg_info, void* stream);
+
 /* ---- next row N2: player byte stream (movie.py, opcodes.py) --------------------- */
 
 /* Movie.emit_stream (movie.py:122-161) with Machine.emit (machine.py:11-25) and the

@@ -120,3 +120,24 @@ def test_bad_schedule_rejected(ops, device_tables):
     for segs in ([(1, 0, 5)], [(0, 1, 5)], [(0, 0, 100000)]):
         with pytest.raises(IIVError):
             ops.encode_clips("HGR", states, tmem, tp, segs, device_tables("HGR"))
+
+
+def test_planned_schedule_equals_plain_call(ops, device_tables):
+    """iiv_encode_clips_planned (schedule resident on the device) = iiv_encode_clips."""
+    import torch
+    from encoder_util import seed_states
+    from iivision_b200.synth import movie_schedule, synthetic_frames
+    mode = "DHGR"
+    frames = synthetic_frames(mode, 2, 0.6, seed=21)[None]
+    segs = movie_schedule(mode, 2, opcodes_per_frame=300, flip_every=110)
+    tmem = torch.from_numpy(frames).cuda()
+    tpacked = ops.pack(mode, tmem[0, :, 0].contiguous(), tmem[0, :, 1].contiguous()).view(1, 2, 32, 128)
+    outs = []
+    for plan in (segs, ops.SegmentPlan(segs)):
+        st = ops.new_clip_states(1)
+        seed_states(ops, st, [9])
+        opc, info = ops.encode_clips(mode, st, tmem, tpacked, plan, device_tables(mode))
+        torch.cuda.synchronize()
+        outs.append((opc.cpu().numpy(), info.cpu().numpy()[..., :4], st.cpu().numpy()))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
