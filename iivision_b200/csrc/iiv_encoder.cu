@@ -70,7 +70,7 @@ struct Smem {
   int32_t scan[kThreads / 32];
   uint32_t hist[kThreads / 32][257];   // per-warp digit histograms of the heap select
   uint64_t sel_prefix;
-  int sel_remaining, sel_count;
+  int sel_remaining, sel_count, sel_done, sel_expect;
   // phase B: rows of new diffs (compute_delta_page's new_diff, video.py:281) for
   // upcoming heap entries, filled by the producer warps.  Slot kRing is the
   // consumer's own (re-queued cells are scored on demand).
@@ -454,11 +454,20 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) diff |= sm.wmin64[w];
         const int top_shift = diff ? ((63 - __clzll((long long)diff)) >> 3) << 3 : 0;
+        // The sort pads to a power of two anyway, so the select may stop as soon as the
+        // whole bucket holding the need-th key fits in that padding: `need` keys are still
+        // guaranteed, a few more ride along for free.
+        int cap = 256;
+        while (cap < need) cap <<= 1;
+        if (cap > kPushedCap) cap = kPushedCap;
         if (t == 0) {
           sm.sel_prefix = (sm.keys[0] >> (top_shift + 8)) << (top_shift + 8);
           sm.sel_remaining = need;
+          sm.sel_done = 0;
+          sm.sel_expect = need;
         }
-        for (int shift = top_shift; shift >= 0; shift -= 8) {
+        __syncthreads();
+        for (int shift = top_shift; shift >= 0 && !sm.sel_done; shift -= 8) {
           for (int k = t; k < (kThreads / 32) * 257; k += kThreads) (&sm.hist[0][0])[k] = 0;
           __syncthreads();
           const uint64_t prefix = sm.sel_prefix;
@@ -493,8 +502,16 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 if (run < (uint32_t)remaining && (uint32_t)remaining <= run + c[q]) {
-                  sm.sel_prefix = prefix | ((uint64_t)(8 * lane + q) << shift);
-                  sm.sel_remaining = remaining - (int)run;
+                  const uint64_t pre = prefix | ((uint64_t)(8 * lane + q) << shift);
+                  const int taken = need - remaining + (int)run;   // keys below this bucket
+                  if (taken + (int)c[q] <= cap && shift > 0) {
+                    sm.sel_prefix = pre | ((1ull << shift) - 1ull);   // the whole bucket
+                    sm.sel_expect = taken + (int)c[q];
+                    sm.sel_done = 1;
+                  } else {
+                    sm.sel_prefix = pre;
+                    sm.sel_remaining = remaining - (int)run;
+                  }
                 }
                 run += c[q];
               }
@@ -502,9 +519,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           }
           __syncthreads();
         }
-        // compact the keys <= threshold (exactly `need` of them) through the re-queue
+        // compact the keys <= threshold (sel_expect >= need of them) through the re-queue
         // buffer, which is idle until phase B
         const uint64_t threshold = sm.sel_prefix;
+        const int n_sel = sm.sel_expect;
         if (t == 0) sm.sel_count = 0;
         __syncthreads();
         for (int k0 = 0; k0 < n_heap; k0 += kThreads) {
@@ -518,9 +536,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           if (keep) sm.pushed[basepos + __popc(bal & ((1u << lane) - 1u))] = key;
         }
         __syncthreads();
-        n_sorted = need;
-        if (sm.sel_count != need) error_flags |= 2;   // cannot happen: keys are unique
-        for (int k = t; k < need; k += kThreads) sm.keys[k] = sm.pushed[k];
+        n_sorted = n_sel;
+        if (sm.sel_count != n_sel) error_flags |= 2;   // cannot happen: keys are unique
+        for (int k = t; k < n_sel; k += kThreads) sm.keys[k] = sm.pushed[k];
         __syncthreads();
       }
     }
