@@ -247,6 +247,36 @@ __device__ __forceinline__ uint64_t warp_min64(uint64_t v) {
   return ((uint64_t)mh << 32) | ml;
 }
 
+// Bitonic steps of partner distance <= 32 on one 64-key chunk, for the network phases
+// k_lo .. k_hi (powers of two; phases above 64 contribute their last six steps only).
+// `base` is the chunk's index in the whole array: the direction of a compare-exchange
+// is ascending where (index & k) == 0.  Lane l holds keys l and l + 32 of the chunk.
+__device__ __forceinline__ void sort_chunk64(uint64_t* chunk, int base, int lane, int k_lo,
+                                             int k_hi) {
+  uint64_t e0 = chunk[lane], e1 = chunk[lane + 32];
+  for (int k = k_lo; k <= k_hi; k <<= 1) {
+    const bool asc0 = ((base + lane) & k) == 0;
+    const bool asc1 = ((base + lane + 32) & k) == 0;
+    if (k >= 64) {   // distance 32: the lane's own pair (same direction for both)
+      if ((e0 > e1) == asc0) {
+        const uint64_t x = e0;
+        e0 = e1;
+        e1 = x;
+      }
+    }
+    for (int j = min(k >> 1, 16); j > 0; j >>= 1) {
+      const uint64_t p0 = __shfl_xor_sync(0xffffffffu, e0, j);
+      const uint64_t p1 = __shfl_xor_sync(0xffffffffu, e1, j);
+      const bool lower = (lane & j) == 0;
+      // the lower index keeps the minimum where the direction is ascending
+      e0 = ((lower == asc0) == (p0 < e0)) ? p0 : e0;
+      e1 = ((lower == asc1) == (p1 < e1)) ? p1 : e1;
+    }
+  }
+  chunk[lane] = e0;
+  chunk[lane + 32] = e1;
+}
+
 template <int MODE>
 __device__ __forceinline__ void apply_store(uint64_t* src, uint8_t* mem, int page,
                                             int offset, int is_aux, uint32_t value) {
@@ -547,8 +577,14 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     while (P < n_sorted) P <<= 1;
     for (int k = n_sorted + t; k < P; k += kThreads) sm.keys[k] = kDead;
     __syncthreads();
-    for (int k = 2; k <= P; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
+    // Bitonic network.  Steps whose partner distance is below 64 never leave a 64-key
+    // chunk, so a warp runs all of them back to back on a chunk held in registers (two
+    // keys per lane, shuffles for distances < 32); only the wider steps go through
+    // shared memory with a block barrier: 15 barriers for 1024 keys instead of 55.
+    for (int c = warp; c < P / 64; c += kWarps) sort_chunk64(sm.keys + 64 * c, 64 * c, lane, 2, 64);
+    __syncthreads();
+    for (int k = 128; k <= P; k <<= 1) {
+      for (int j = k >> 1; j >= 64; j >>= 1) {
         for (int idx = t; idx < P / 2; idx += kThreads) {
           const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));
           const int l = i | j;
@@ -561,6 +597,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         }
         __syncthreads();
       }
+      for (int c = warp; c < P / 64; c += kWarps) sort_chunk64(sm.keys + 64 * c, 64 * c, lane, k, k);
+      __syncthreads();
     }
     const int n_first = n_sorted;   // entries of the sorted array phase B may walk
 
@@ -1120,6 +1158,17 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       }
     } else if (warp == kTwistWarp) {
       int done = 0;
+      // Idle time goes into warming L2 for the next segment's scoring pass: its 8192
+      // table gathers are addressed by (source window, target window), and all but the
+      // few hundred cells this segment still rewrites already hold their final source
+      // bytes.  Prefetches only -- nothing is read back, so a stale address costs a miss
+      // later and nothing else.
+      const uint64_t* pf_tp = nullptr;
+      int pf_aux = 0, pf_col = 0;
+      if (seg + 1 < n_segments && segments[3 * seg + 5] > 0) {
+        pf_aux = segments[3 * seg + 4];
+        pf_tp = target_packed + ((size_t)clip * n_frames + segments[3 * seg + 3]) * kCols;
+      }
       while (true) {
         int req = 0, st = 0;
         if (lane == 0) {
@@ -1139,6 +1188,23 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           if (lane == 0) sm.mt_done = done;
         } else if (st) {
           break;
+        } else if (pf_tp != nullptr && pf_col < kCols) {
+          uint64_t g[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) g[q] = __ldg(pf_tp + pf_col + 32 * q + lane);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint64_t s = sm.src[pf_col + 32 * q + lane];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int o = byte_offset<MODE>(half, pf_aux);
+              const uint32_t x = mask_shift<MODE>(s, o), y = mask_shift<MODE>(g[q], o);
+              const uint16_t* addr =
+                  table + (((uint32_t)o << (2 * M::kBits)) + (x << M::kBits) + y);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
+            }
+          }
+          pf_col += 128;
         } else {
           __nanosleep(200);
         }
