@@ -101,6 +101,7 @@ struct Smem {
   volatile int stop;              // segment finished: producers leave
   volatile int mt_req, mt_done;   // stream P block twists requested / finished
   volatile int mt_src;            // buffer to twist from
+  volatile int np_pre;            // successor blocks of stream N prepared during phase B
 };
 
 __device__ __forceinline__ void twist(const uint32_t* __restrict__ s,
@@ -118,6 +119,7 @@ __device__ __forceinline__ void twist(const uint32_t* __restrict__ s,
 // The same generation step done by a single warp (phase B helper warp).
 // Also stores getrandbits(8) = top byte of each tempered new word into the block's
 // slot(s) of py_nonce (slot s < 3 holds block numbers s mod 3; slot 3 repeats slot 0).
+template <bool kNonces>
 __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
                                            uint32_t* __restrict__ d, int lane, int slot,
                                            uint8_t* __restrict__ py_nonce) {
@@ -131,7 +133,7 @@ __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
     if (t < 227) {
       const uint32_t w = mt_mix(s[t], s[t + 1], s[t + 397]);
       d[t] = w;
-      nb[t] = nb2[t] = (uint8_t)(mt_temper(w) >> 24);
+      if (kNonces) nb[t] = nb2[t] = (uint8_t)(mt_temper(w) >> 24);
     }
   }
   __syncwarp();
@@ -141,7 +143,7 @@ __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
     if (t < 227) {
       const uint32_t w = mt_mix(s[227 + t], s[228 + t], d[t]);
       d[227 + t] = w;
-      nb[227 + t] = nb2[227 + t] = (uint8_t)(mt_temper(w) >> 24);
+      if (kNonces) nb[227 + t] = nb2[227 + t] = (uint8_t)(mt_temper(w) >> 24);
     }
   }
   __syncwarp();
@@ -151,13 +153,13 @@ __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
     if (t < 169) {
       const uint32_t w = mt_mix(s[454 + t], s[455 + t], d[227 + t]);
       d[454 + t] = w;
-      nb[454 + t] = nb2[454 + t] = (uint8_t)(mt_temper(w) >> 24);
+      if (kNonces) nb[454 + t] = nb2[454 + t] = (uint8_t)(mt_temper(w) >> 24);
     }
   }
   if (lane == 0) {
     const uint32_t w = mt_mix(s[623], d[0], d[396]);
     d[623] = w;
-    nb[623] = nb2[623] = (uint8_t)(mt_temper(w) >> 24);
+    if (kNonces) nb[623] = nb2[623] = (uint8_t)(mt_temper(w) >> 24);
   }
   __syncwarp();
 }
@@ -321,6 +323,13 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     sm.mt_py[0][k] = g_mt_py[k];
   }
   int np_cur = 0;                 // which ping-pong buffer holds stream N
+  // Successor blocks of stream N that the twister warp generated during the previous
+  // segment's opcode loop; they live in the upper half of the heap array, which phase B
+  // does not use when the sorted prefix is at most 4096 keys.
+  constexpr int kNpPreMax = 13;   // (623 + 7680 - 1) / 624 blocks at most per segment
+  uint32_t* const np_pre_blocks = reinterpret_cast<uint32_t*>(&sm.keys[kCells / 2]);
+  static_assert(kNpPreMax * 624 * 4 <= (kCells / 2) * 8, "pre-twisted blocks do not fit");
+  int np_ready = 0;
   int pos_np = (int)g_mt_np[624]; // 0..624
   int pos_py = (int)g_mt_py[624];
   // Three blocks of stream P stay resident (ring of buffers, slot = block number mod 3):
@@ -438,16 +447,28 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     uint8_t* np_nonce = reinterpret_cast<uint8_t*>(&sm.ring_row[0][0]);
     static_assert(sizeof(sm.ring_row) >= kCells, "nonce scratch too small");
     const int twists = n_heap > 0 ? (pos_np + n_heap - 1) / 624 : 0;
-    for (int b = 0; b <= twists; ++b) {
-      if (b > 0) {
-        twist(sm.mt_np[np_cur], sm.mt_np[np_cur ^ 1]);
-        np_cur ^= 1;
+    {
+      const uint32_t* blk = sm.mt_np[np_cur];
+      for (int b = 0; b <= twists; ++b) {
+        if (b > 0) {
+          if (b <= np_ready) {
+            blk = np_pre_blocks + (b - 1) * 624;
+          } else {
+            twist(blk, sm.mt_np[np_cur ^ 1]);
+            np_cur ^= 1;
+            blk = sm.mt_np[np_cur];
+          }
+        }
+        for (int k = t; k < 624; k += kThreads) {
+          const int g = b * 624 + k - pos_np;
+          if (g >= 0 && g < n_heap) np_nonce[g] = (uint8_t)(mt_temper(blk[k]) & 0xffu);
+        }
       }
-      for (int k = t; k < 624; k += kThreads) {
-        const int g = b * 624 + k - pos_np;
-        if (g >= 0 && g < n_heap)
-          np_nonce[g] = (uint8_t)(mt_temper(sm.mt_np[np_cur][k]) & 0xffu);
-      }
+      // the block the position ends in becomes the resident state (before the keys below
+      // overwrite the prepared blocks)
+      if (blk != sm.mt_np[np_cur])
+        for (int k = t; k < 624; k += kThreads) sm.mt_np[np_cur][k] = blk[k];
+      np_ready = 0;
     }
     __syncthreads();
     {
@@ -483,7 +504,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         diff = 0;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) diff |= sm.wmin64[w];
-        const int top_shift = diff ? ((63 - __clzll((long long)diff)) >> 3) << 3 : 0;
+        // first digit = the eight bits ending at the highest differing one, so that its
+        // 256 buckets are all in use and the boundary bucket is small: one counting pass
+        // usually settles the selection
+        const int top_shift = diff ? max(0, 63 - __clzll((long long)diff) - 7) : 0;
         // The sort pads to a power of two anyway, so the select may stop as soon as the
         // whole bucket holding the need-th key fits in that padding: `need` keys are still
         // guaranteed, a few more ride along for free.
@@ -497,14 +521,17 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           sm.sel_expect = need;
         }
         __syncthreads();
-        for (int shift = top_shift; shift >= 0 && !sm.sel_done; shift -= 8) {
+        // bits >= fixed of the prefix are settled; a digit may overlap them on the last
+        // pass (shift clamped to 0), where its upper bits are then equal for every match
+        for (int shift = top_shift, fixed = top_shift + 8; !sm.sel_done;
+             fixed = shift, shift = max(shift - 8, 0)) {
           for (int k = t; k < (kThreads / 32) * 257; k += kThreads) (&sm.hist[0][0])[k] = 0;
           __syncthreads();
           const uint64_t prefix = sm.sel_prefix;
           const int remaining = sm.sel_remaining;
           for (int k = t; k < n_heap; k += kThreads) {
             const uint64_t key = sm.keys[k];
-            if (((key ^ prefix) >> (shift + 8)) == 0)
+            if (((key ^ prefix) >> fixed) == 0)
               atomicAdd(&sm.hist[warp][(uint32_t)(key >> shift) & 255u], 1u);
           }
           __syncthreads();
@@ -541,6 +568,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
                   } else {
                     sm.sel_prefix = pre;
                     sm.sel_remaining = remaining - (int)run;
+                    if (shift == 0) sm.sel_done = 1;   // pre is the need-th key itself
                   }
                 }
                 run += c[q];
@@ -606,7 +634,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     // The opcode loop is a chain -- each opcode's nonces start where the previous
     // one's ended, and its stores change the priorities the next pop sees -- so it is
     // cut into stages run by specialised warps, none of which crosses a block barrier:
-    //   producers (warps 1-3)  run ahead along the sorted heap and score the row of
+    //   producers (warps 0-2)  run ahead along the sorted heap and score the row of
     //       new diffs of each upcoming entry (two dependent global loads: target word,
     //       table gather) into a ring in shared memory, two entries in flight per warp.
     //       A row depends on the target frame and the content byte only, never on the
@@ -623,13 +651,15 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     //   applier (warp 4)  commits the stores of every published opcode to the source
     //       bitmap and memory map (Bitmap.apply), in order.  Nothing in phase B reads
     //       the source, so this is off the chain.
-    //   twister (warp 0)  prepares the next MT19937 block of stream P in the background.
+    //   twister (warp 3)  prepares the next MT19937 block of stream P in the background and,
+    //       when idle, the next segment's stream N blocks and L2 lines (see below).
     // A cell whose priority is already 0 is skipped by everyone alike: priorities only
     // ever fall to 0 inside a segment (video.py:140, :159-170).
     // The issue arbiter favours the highest warp id of a scheduler and a spinning warp
     // is nearly always eligible, hence the decision warp is 7 and shares its scheduler
-    // (warp id % 4) with a producer, which mostly waits on global loads; the applier and
-    // the twister share scheduler 0; helper loops back off with nanosleep.
+    // (warp id % 4) with the twister, which is idle or streaming through a block most of
+    // the time (swapping it with a producer measured the same); helper loops back off
+    // with nanosleep.
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr int kDecideWarp = 7, kTwistWarp = 3, kApplyWarp = 4;
     constexpr uint32_t kEndOfHeap = 0xffffffffu, kDeadRecord = 0xffffffffu;
@@ -643,6 +673,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       sm.stop = 0;
       sm.mt_req = 0;
       sm.mt_done = 0;
+      sm.np_pre = 0;
       sm.final_emitted = 0;
       sm.applied_pub = 0;
       sm.pop_turn = 0;
@@ -1165,6 +1196,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       // later and nothing else.
       const uint64_t* pf_tp = nullptr;
       int pf_aux = 0, pf_col = 0;
+      // ... and, before that, into the stream N blocks the next heapify will draw from
+      // (one nonce per nonzero priority, video.py:259-267: 13 blocks for a full screen).
+      const int np_goal = (seg + 1 < n_segments && P <= kCells / 2) ? kNpPreMax : 0;
+      int np_made = 0;
       if (seg + 1 < n_segments && segments[3 * seg + 5] > 0) {
         pf_aux = segments[3 * seg + 4];
         pf_tp = target_packed + ((size_t)clip * n_frames + segments[3 * seg + 3]) * kCols;
@@ -1181,13 +1216,18 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           __threadfence_block();
           const int src = sm.mt_src;
           const int dst = src == 2 ? 0 : src + 1;
-          warp_twist(sm.mt_py[src], sm.mt_py[dst], lane, dst, sm.py_nonce);
+          warp_twist<true>(sm.mt_py[src], sm.mt_py[dst], lane, dst, sm.py_nonce);
           ++done;
           __threadfence_block();
           __syncwarp();
           if (lane == 0) sm.mt_done = done;
         } else if (st) {
           break;
+        } else if (np_made < np_goal) {
+          warp_twist<false>(np_made == 0 ? sm.mt_np[np_cur] : np_pre_blocks + (np_made - 1) * 624,
+                            np_pre_blocks + np_made * 624, lane, 0, sm.py_nonce);
+          ++np_made;
+          if (lane == 0) sm.np_pre = np_made;
         } else if (pf_tp != nullptr && pf_col < kCols) {
           uint64_t g[4];
 #pragma unroll
@@ -1211,6 +1251,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       }
     }
     __syncthreads();
+    np_ready = sm.np_pre;
     emitted = sm.scan[0];
     out_of_work = sm.scan[1] != 0;
     py_words = sm.scan[2];
