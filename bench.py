@@ -339,6 +339,10 @@ def scorer_figures(torch, ops, single=True):
         out.update(hgr_clip_and_cpu(torch, ops, table_dhgr=table))
     except Exception as e:   # noqa: BLE001
         out["hgr_clip_error"] = repr(e)
+    try:
+        out.update(facade_figures(torch))
+    except Exception as e:   # noqa: BLE001
+        out["facade_error"] = repr(e)
     ms1, all1, trace1 = encode_run(1, 16)
     out["single_clip_trace"] = trace1
     out["single_clip_frames_per_s"] = 16 / (ms1 * 1e-3)
@@ -347,6 +351,64 @@ def scorer_figures(torch, ops, single=True):
                                "292) on one SM; median of %d runs (ms: %s)" % (
                                    len(all1), ", ".join("%.2f" % x for x in all1)))
     return out
+
+
+def facade_figures(torch, n_frames=8):
+    """The reference-facing call for path 2: video.Video.encode_frame pulled the way
+    Movie.encode pulls it (a new generator per frame and per bank flip, one next() per
+    audio tick), host arrays in and out -- targets are built from host memory maps, the
+    encoder state and both global MT19937 generators are uploaded per generator and
+    written back at its commit, opcode tuples are read on the host."""
+    import contextlib
+    import io
+    import random
+    import numpy as np
+    from iivision_b200 import palette, screen, synth, video, video_mode
+
+    class Grabber:
+        input_frame_rate = 30
+
+    frames = synth.synthetic_frames("DHGR", n_frames + 1, 1.0, seed=100)
+    segs = synth.movie_schedule("DHGR", n_frames + 1)
+    random.seed(0)
+    np.random.seed(0)
+    v = video.Video(Grabber(), 14700., mode=video_mode.VideoMode.DHGR,
+                    palette=palette.Palette.NTSC)
+    pulled = 0
+    t0 = None
+    op_seq = None
+    h2d = d2h = 0
+    tgt, tgt_frame = None, -1
+    with contextlib.redirect_stdout(io.StringIO()):
+        for frame, is_aux, budget in segs:
+            if frame == 1 and t0 is None:      # frame 0 is the warm-up
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            if frame != tgt_frame:             # one target bitmap per frame (movie.py:81-91)
+                tgt_frame = frame
+                tgt = screen.DHGRBitmap(
+                    palette=palette.Palette.NTSC,
+                    main_memory=screen.MemoryMap(1, frames[frame, 0].copy()),
+                    aux_memory=screen.MemoryMap(1, frames[frame, 1].copy()))
+            op_seq = v.encode_frame(tgt, is_aux=bool(is_aux))
+            for _ in range(budget):
+                next(op_seq)
+            if t0 is not None:
+                pulled += budget
+                # per generator: state up (packed, 2 maps, 2 priorities, 2 MT blobs) and
+                # target up; opcodes, segment info and state down
+                h2d += 32 * 128 * 8 + 2 * 8192 + 2 * 32768 + 2 * 2560 + 2 * 8192 + 32768
+                d2h += budget * 8 + 64 + 32 * 128 * 8 + 2 * 8192 + 2 * 32768 + 2 * 2560 + 64
+        op_seq.close()
+        torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"facade_frames_per_s": n_frames / dt,
+            "facade_us_per_opcode": dt * 1e6 / pulled,
+            "facade_h2d_bytes_per_frame": h2d // n_frames,
+            "facade_d2h_bytes_per_frame": d2h // n_frames,
+            "facade_note": ("video.Video.encode_frame under the Movie.encode schedule, %d DHGR "
+                            "frames after one warm-up frame, %d generators, host arrays in and "
+                            "out; wall clock" % (n_frames, sum(1 for s_ in segs if s_[0] > 0)))}
 
 
 def hgr_clip_and_cpu(torch, ops, table_dhgr):

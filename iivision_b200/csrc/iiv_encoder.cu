@@ -29,6 +29,8 @@
 //    with a non-zero residual draws one more (video.py:290-293, :173-178).
 //  * at most two further offsets are accepted (len(offsets) == 3 -> break,
 //    video.py:181); the fourth slot repeats the first.
+#include <mutex>
+
 #include "iiv_common.cuh"
 
 namespace iiv {
@@ -1397,6 +1399,35 @@ static int check_encode_args(int mode, int n_clips, const void* d_state, size_t 
   return 0;
 }
 
+// Stream-ordered scratch for the schedule of an unplanned call.  The device's default
+// pool hands its pages back to the OS at every synchronisation (release threshold 0), which
+// turns the next cudaMallocAsync into a real allocation of a millisecond or more; a pool of
+// our own that keeps what it has makes the call allocation-free after the first one.
+static cudaError_t scratch_pool(cudaMemPool_t* out) {
+  constexpr int kMaxDevices = 64;
+  static std::mutex mu;
+  static cudaMemPool_t pools[kMaxDevices] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    e = cudaMemPoolCreate(&pools[dev], &props);
+    if (e != cudaSuccess) return e;
+    uint64_t keep = ~0ull;
+    e = cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) return e;
+  }
+  *out = pools[dev];
+  return cudaSuccess;
+}
+
 extern "C" int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
                                 size_t state_stride, const uint8_t* d_target_mem,
                                 const uint64_t* d_target_packed, int n_frames,
@@ -1414,7 +1445,10 @@ extern "C" int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
   IIV_REQUIRE(d_opcodes || total == 0, "null opcode buffer");
   cudaStream_t st = (cudaStream_t)stream;
   int32_t* d_segments = nullptr;
-  IIV_CUDA(cudaMallocAsync(&d_segments, sizeof(int32_t) * 3 * n_segments, st));
+  cudaMemPool_t pool;
+  IIV_CUDA(scratch_pool(&pool));
+  IIV_CUDA(cudaMallocFromPoolAsync((void**)&d_segments, sizeof(int32_t) * 3 * n_segments, pool,
+                                   st));
   cudaError_t e = cudaMemcpyAsync(d_segments, h_segments, sizeof(int32_t) * 3 * n_segments,
                                   cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess)

@@ -414,7 +414,7 @@ def mt_from_python(state) -> np.ndarray:
 
 
 def mt_to_python(words625: np.ndarray):
-    return (3, tuple(int(x) for x in words625), None)
+    return (3, tuple(np.asarray(words625).tolist()), None)
 
 
 def mt_from_numpy(state) -> np.ndarray:

@@ -21,6 +21,13 @@ global ``random`` / ``np.random`` generators are advanced to where the reference
 would have left them.  Between those commit points the host arrays and global RNGs
 lag behind; call ``Video.sync()`` to force a commit mid-generator.
 
+The speculated budget is a guess at how many opcodes the caller will pull before it
+abandons the generator; ``Movie.encode`` does so at every bank flip (a fixed number of
+opcodes apart) and at every new frame, so the guess is learnt from the generators seen
+so far (``Video._predict``).  A wrong guess costs one more launch, never a different
+result.  Per generator the host side moves one state blob up and one down through
+page-locked staging buffers; the launch itself allocates nothing.
+
 For throughput (many clips, known schedules) use ``ops.encode_clips`` directly.
 """
 
@@ -75,8 +82,25 @@ class Video:
         # Movie.encode restarts the generator every 292 opcodes in DHGR (2 KiB of
         # stream) and every 980 at most in HGR (movie.py:94-102)
         self.speculate = int(speculate or (292 if mode == VideoMode.DHGR else 980))
+        self._adaptive = speculate is None
         self._state = ops.new_clip_states(1)
         self._live = None   # the _Run of the generator currently being pulled
+        # page-locked staging: the state blob on its way up / down, opcode records and
+        # segment info on their way down
+        self._stage_up = torch.zeros(ops.STATE_BYTES, dtype=torch.uint8, pin_memory=True)
+        self._stage_down = torch.zeros(ops.STATE_BYTES, dtype=torch.uint8, pin_memory=True)
+        self._stage_ops = torch.zeros(MAX_BUDGET * 8, dtype=torch.uint8, pin_memory=True)
+        self._stage_info = torch.zeros(8, dtype=torch.int64, pin_memory=True)
+        self._d_ops = torch.empty((1, MAX_BUDGET, 8), dtype=torch.uint8, device="cuda")
+        self._d_info = torch.zeros((1, 1, 8), dtype=torch.int64, device="cuda")
+        self._plans = {}
+        # pull statistics behind _predict
+        self._last_target = None
+        self._last_aux = None
+        self._since_flip = 0       # opcodes pulled since the bank last changed
+        self._since_frame = 0      # ... since the target last changed
+        self._flip_period = None   # opcodes between the last two bank changes
+        self._frame_period = None  # opcodes pulled for the last complete target
 
     def tick(self, ticks: int) -> bool:
         """Keep track of when it is time for a new image frame."""
@@ -86,49 +110,82 @@ class Video:
         return False
 
     # -- host <-> device state ---------------------------------------------------------
-    def _field(self, f, dtype, shape):
-        return ops.state_field(self._state, f, dtype, shape)[0]
+    @staticmethod
+    def _host_field(blob: np.ndarray, f, dtype, shape) -> np.ndarray:
+        off = ops.STATE_OFFSETS[f]
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return blob[off:off + n].view(dtype).reshape(shape)
 
     def _upload(self):
-        st = self._state
-        st.zero_()
-        self._field(ops.F_PACKED, torch.int64, (32, 128)).copy_(
-            torch.from_numpy(self.pixelmap.packed.view(np.int64)))
-        self._field(ops.F_MAIN, torch.uint8, (32, 256)).copy_(
-            torch.from_numpy(self.memory_map.page_offset))
-        self._field(ops.F_PRIO_MAIN, torch.int32, (32, 256)).copy_(
-            torch.from_numpy(self.update_priority))
+        """Host arrays and the process-global generators -> the device state blob."""
+        blob = self._stage_up.numpy()
+        blob[:] = 0
+        hf = self._host_field
+        hf(blob, ops.F_PACKED, np.uint64, (32, 128))[...] = self.pixelmap.packed
+        hf(blob, ops.F_MAIN, np.uint8, (32, 256))[...] = self.memory_map.page_offset
+        hf(blob, ops.F_PRIO_MAIN, np.int32, (32, 256))[...] = self.update_priority
         if self.mode == VideoMode.DHGR:
-            self._field(ops.F_AUX, torch.uint8, (32, 256)).copy_(
-                torch.from_numpy(self.aux_memory_map.page_offset))
-            self._field(ops.F_PRIO_AUX, torch.int32, (32, 256)).copy_(
-                torch.from_numpy(self.aux_update_priority))
-        mt = np.zeros(640, np.uint32)
-        mt[:625] = ops.mt_from_numpy(np.random.get_state())
-        self._field(ops.F_MT_NP, torch.int32, (640,)).copy_(torch.from_numpy(mt.view(np.int32)))
-        mt[:625] = ops.mt_from_python(random.getstate())
-        self._field(ops.F_MT_PY, torch.int32, (640,)).copy_(torch.from_numpy(mt.view(np.int32)))
+            hf(blob, ops.F_AUX, np.uint8, (32, 256))[...] = self.aux_memory_map.page_offset
+            hf(blob, ops.F_PRIO_AUX, np.int32, (32, 256))[...] = self.aux_update_priority
+        hf(blob, ops.F_MT_NP, np.uint32, (625,))[...] = ops.mt_from_numpy(np.random.get_state())
+        hf(blob, ops.F_MT_PY, np.uint32, (625,))[...] = ops.mt_from_python(random.getstate())
+        self._state[0].copy_(self._stage_up, non_blocking=True)
 
-    def _download(self, state: torch.Tensor):
-        host = state.cpu()
-
-        def field(f, dtype, shape):
-            return ops.state_field(host, f, dtype, shape)[0].numpy()
-        self.pixelmap.packed[...] = field(ops.F_PACKED, torch.int64, (32, 128)).view(np.uint64)
-        self.memory_map.page_offset[...] = field(ops.F_MAIN, torch.uint8, (32, 256))
-        self.update_priority[...] = field(ops.F_PRIO_MAIN, torch.int32, (32, 256))
+    def _download(self, blob: np.ndarray):
+        """A state blob brought back by _Run._run -> host arrays and global generators."""
+        hf = self._host_field
+        self.pixelmap.packed[...] = hf(blob, ops.F_PACKED, np.uint64, (32, 128))
+        self.memory_map.page_offset[...] = hf(blob, ops.F_MAIN, np.uint8, (32, 256))
+        self.update_priority[...] = hf(blob, ops.F_PRIO_MAIN, np.int32, (32, 256))
         if self.mode == VideoMode.DHGR:
-            self.aux_memory_map.page_offset[...] = field(ops.F_AUX, torch.uint8, (32, 256))
-            self.aux_update_priority[...] = field(ops.F_PRIO_AUX, torch.int32, (32, 256))
-        mt_np = field(ops.F_MT_NP, torch.int32, (640,)).view(np.uint32)[:625]
-        mt_py = field(ops.F_MT_PY, torch.int32, (640,)).view(np.uint32)[:625]
-        np.random.set_state(ops.mt_to_numpy(mt_np))
-        random.setstate(ops.mt_to_python(mt_py))
-        flags = int(field(ops.F_FLAGS, torch.int32, (8,))[2])
+            self.aux_memory_map.page_offset[...] = hf(blob, ops.F_AUX, np.uint8, (32, 256))
+            self.aux_update_priority[...] = hf(blob, ops.F_PRIO_AUX, np.int32, (32, 256))
+        np.random.set_state(ops.mt_to_numpy(hf(blob, ops.F_MT_NP, np.uint32, (625,))))
+        random.setstate(ops.mt_to_python(hf(blob, ops.F_MT_PY, np.uint32, (625,))))
+        flags = int(hf(blob, ops.F_FLAGS, np.int32, (8,))[2])
         if flags & 1:
             raise AssertionError("DHGR content byte with bit 7 set")   # video.py:135-137
         if flags & ~1:
             raise RuntimeError("encoder kernel internal error %#x" % flags)
+
+    def _plan(self, is_aux: bool, budget: int) -> ops.SegmentPlan:
+        key = (bool(is_aux), int(budget))
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) > 4096:
+                self._plans.clear()
+            plan = self._plans[key] = ops.SegmentPlan([(0, int(is_aux), int(budget))])
+        return plan
+
+    # -- how many opcodes will this generator be asked for? ----------------------------------
+    def _predict(self, target, is_aux: bool) -> int:
+        """Movie.encode (movie.py:94-102) drops a generator at every bank flip, a fixed
+        number of opcodes after the previous one, and at every new frame.  Both periods are
+        taken from what the caller did so far; until they are known the guess is
+        ``speculate``."""
+        if not self._adaptive:
+            return self.speculate
+        new_frame = target is not self._last_target
+        flipped = self._last_aux is not None and bool(is_aux) != self._last_aux
+        if new_frame and self._last_target is not None:
+            self._frame_period = self._since_frame
+            self._since_frame = 0
+        if flipped:
+            self._flip_period = self._since_flip
+            self._since_flip = 0
+        self._last_target, self._last_aux = target, bool(is_aux)
+        guess = self.speculate
+        if self.mode == VideoMode.DHGR:
+            period = self._flip_period or self.speculate
+            if period > self._since_flip:
+                guess = period - self._since_flip
+        if self._frame_period and self._frame_period > self._since_frame:
+            guess = min(guess, self._frame_period - self._since_frame)
+        return max(1, min(guess, MAX_BUDGET))
+
+    def _pulled(self, n: int) -> None:
+        self._since_flip += n
+        self._since_frame += n
 
     # -- encode_frame ------------------------------------------------------------------------
     def encode_frame(self, target: screen.Bitmap, is_aux: bool
@@ -172,6 +229,7 @@ class _Run:
         self.pulled = 0
         self.closed = False
         m = video._mode_name
+        guess = video._predict(target, is_aux)
         video._upload()
         self.snapshot = video._state.clone()
         banks = [target.main_memory.page_offset]
@@ -186,31 +244,37 @@ class _Run:
         self.budget = 0
         self.ops = None
         self.real = 0
-        self.state_after = None
-        self._run(min(video.speculate, MAX_BUDGET))
+        self.state_after = None      # host copy of the state blob after `budget` opcodes
+        self._run(guess)
 
     def _run(self, budget: int):
+        v = self.v
         state = self.snapshot.clone()
-        opc, info = ops.encode_clips(self.v._mode_name, state, self.tmem, self.tpacked,
-                                     [(0, int(self.is_aux), budget)], self.table)
+        d_ops = v._d_ops[:, :budget]
+        ops.encode_clips(v._mode_name, state, self.tmem, self.tpacked,
+                         v._plan(self.is_aux, budget), self.table,
+                         opcodes=d_ops, seg_info=v._d_info)
+        v._stage_ops[:budget * 8].copy_(d_ops.reshape(-1), non_blocking=True)
+        v._stage_info.copy_(v._d_info.view(-1), non_blocking=True)
+        v._stage_down.copy_(state[0], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        self.ops = opc.cpu().numpy()[0]
-        self.real = int(info.cpu().numpy()[0, 0, 0])
+        self.ops = v._stage_ops[:budget * 8].numpy().reshape(budget, 8).tolist()
+        self.real = int(v._stage_info[0])
         self.budget = budget
-        self.state_after = state
+        self.state_after = v._stage_down.numpy().copy()
 
     def opcode(self, k: int):
         if k >= self.budget and self.real == self.budget:
             if self.budget >= MAX_BUDGET:
                 raise NotImplementedError(
                     "more than %d opcodes pulled from one encode_frame generator" % MAX_BUDGET)
-            self._run(min(2 * self.budget, MAX_BUDGET))
+            self._run(min(max(2 * self.budget, self.v.speculate), MAX_BUDGET))
         if k >= self.real:
             # out of work: (32, target[0, 0], [0, 0, 0, 0]) forever (video.py:249-251)
             self.v.out_of_work[self.is_aux] = True
             return self.pad
         r = self.ops[k]
-        return int(r[0]), int(r[1]), [int(r[2]), int(r[3]), int(r[4]), int(r[5])]
+        return r[0], r[1], r[2:6]
 
     def commit(self, keep: bool = False):
         if self.closed:
@@ -221,9 +285,9 @@ class _Run:
                 pass                      # ran dry: state_after is final whatever k is
             elif k != self.budget:
                 self._run(k)
-            self.v._state.copy_(self.state_after)
             self.v._download(self.state_after)
         if not keep:
             self.closed = True
+            self.v._pulled(k)
             if self.v._live is self:
                 self.v._live = None

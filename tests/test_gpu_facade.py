@@ -201,6 +201,51 @@ def test_video_sync_mid_generator(mods, oracle_tables):
     assert v.tick(0) and not v.tick(1) and v.tick(490)
 
 
+def test_video_budget_prediction(mods, oracle_tables, monkeypatch):
+    """Pulled the way Movie.encode pulls (one target per frame, a new generator per bank
+    flip and per frame), the facade learns both periods: after the first frame every
+    generator is one kernel run of exactly the opcodes pulled -- and the stream still
+    equals the oracle's."""
+    from iivision_b200 import synth
+    from oracle import scorer
+    n_frames = 3
+    frames = synth.synthetic_frames("DHGR", n_frames, 0.5, seed=21)
+    segs = synth.movie_schedule("DHGR", n_frames)
+    random.seed(5)
+    np.random.seed(5)
+    v = mods.video.Video(_Grabber(), 14700., mode=mods.video_mode.VideoMode.DHGR)
+    ov = scorer.OracleVideo("DHGR", oracle_tables("DHGR"), py_rng=random.Random(5),
+                            np_rng=np.random.RandomState(5))
+    runs = []
+    real_run = mods.video._Run._run
+    monkeypatch.setattr(mods.video._Run, "_run",
+                        lambda self, budget: (runs.append(budget), real_run(self, budget))[1])
+    tgt = otgt = None
+    tgt_frame = -1
+    first_frame_runs = None
+    with contextlib.redirect_stdout(io.StringIO()):
+        for frame, is_aux, budget in segs:
+            if frame != tgt_frame:
+                if frame == 1:
+                    first_frame_runs = len(runs)
+                tgt_frame = frame
+                tgt = mods.screen.DHGRBitmap(
+                    palette=mods.palette.Palette.NTSC,
+                    main_memory=mods.screen.MemoryMap(1, frames[frame, 0].copy()),
+                    aux_memory=mods.screen.MemoryMap(1, frames[frame, 1].copy()))
+                otgt = ov.target_bitmap(frames[frame, 0], frames[frame, 1])
+            seq, oseq = v.encode_frame(tgt, bool(is_aux)), ov.encode_frame(otgt, bool(is_aux))
+            for _ in range(budget):
+                a, b = next(seq), next(oseq)
+                assert (a[0], a[1], a[2]) == (int(b[0]), int(b[1]), [int(x) for x in b[2]])
+            seq.close()
+    later = [s_ for s_ in segs if s_[0] >= 1]
+    assert runs[first_frame_runs:] == [s_[2] for s_ in later]
+    assert np.array_equal(v.update_priority, ov.update_priority)
+    assert np.array_equal(v.aux_update_priority, ov.aux_update_priority)
+    assert np.array_equal(v.pixelmap.packed, ov.pixelmap.packed)
+
+
 def test_static_helpers_against_reference_fixture(mods):
     """_make_header / _make_footer / _body / _fix_column_* / _double_pixels against
     outputs of the reference classes (tests/golden/helpers.npz)."""
