@@ -67,3 +67,29 @@ def test_random_configurations(oracle_tables, device_tables, case):
     assert np.array_equal(pm.cpu().numpy(), v.update_priority)
     mt_py = ops.state_field(states, ops.F_MT_PY, torch.int32, (640,))[0]
     assert ops.mt_to_python(mt_py.cpu().numpy().view(np.uint32)[:625])[1] == py.getstate()[1]
+
+
+@pytest.mark.parametrize("mode,fraction", [("DHGR", 1.0), ("DHGR", 0.1), ("HGR", 1.0)])
+def test_large_budgets_between_small_ones(oracle_tables, device_tables, mode, fraction):
+    """Budgets above a third of the heap switch the prefix selection off (the whole heap is
+    sorted and fills the key array, so nothing can be prepared for the next segment behind
+    it); smaller ones before and after switch it back on."""
+    from iivision_b200 import ops
+    from iivision_b200.synth import synthetic_frames
+    frames = synthetic_frames(mode, 3, fraction, seed=77)
+    a = 1 if mode == "DHGR" else 0
+    segs = [(0, 0, 292), (0, a, 1400), (1, 0, 2048), (1, a, 292), (2, 0, 5), (2, a, 1366),
+            (2, 0, 1365)]
+    want_ops, want_real, v, py, npr = run_oracle(mode, oracle_tables(mode), frames, segs, 11)
+    got, info, states = run_device(ops, mode, device_tables(mode), frames[None], segs, [11])
+    assert np.array_equal(got[0][:, :6].astype(np.int64), want_ops)
+    assert np.array_equal(got[0][:, 6], want_real)
+    import torch
+    mt_np = ops.state_field(states, ops.F_MT_NP, torch.int32, (640,))[0]
+    st = npr.get_state()
+    words = mt_np.cpu().numpy().view(np.uint32)
+    # same position in stream N: the next draws agree
+    from iivision_b200.ops import mt_to_numpy
+    r = np.random.RandomState()
+    r.set_state(mt_to_numpy(words[:625]))
+    assert np.array_equal(r.randint(0, 256, 8), npr.randint(0, 256, 8)), st[2]
