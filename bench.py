@@ -669,6 +669,19 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    # the e2e step is the device-to-host copy of the table: time that copy alone, same
+    # page-locked destination, so the figure can be read against this box's PCIe rate
+    d2h_ms = None
+    if world == 1 and res is not None:
+        dst = torch.from_numpy(res)
+        evc = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        if dst.is_pinned():
+            evc[0].record()
+            dst.view(torch.int16).copy_(table.view(torch.int16).view(dst.shape), non_blocking=True)
+            evc[1].record()
+            torch.cuda.synchronize()
+            d2h_ms = evc[0].elapsed_time(evc[1])
+        del dst
     del res
     if sampler:
         sampler.stop()
@@ -703,6 +716,8 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": 16 * 3 + 256 * 4,
                 "d2h_bytes_per_step": (2 * ENTRIES if world == 1 else shard) + 256 * 4,
                 "steps": e2e_steps,
+                **({"d2h_copy_ms": d2h_ms,
+                    "d2h_copy_gbs": 2.0 * ENTRIES / (d2h_ms * 1e-3) / 1e9} if d2h_ms else {}),
                 "call": "make_data_tables.compute_substitute_costs + compute_edit_distance "
                         "-> host uint16 array" if world == 1 else
                         "per-rank row block generate + D2H of that block"},
