@@ -764,6 +764,31 @@ def run_ours(args, rank, world, local_rank):
             del outs
         except Exception as e:
             line["all_four_tables"] = {"error": repr(e)}
+    if world == 1 and not args.no_scorer:
+        # make_edit_distance end to end: LUT + table + D2H + the reference's compressed .npz
+        # (make_data_tables.py:177-188); the deflate runs on all host cores (npz_io.py)
+        try:
+            import tempfile
+            with tempfile.TemporaryDirectory() as tmp:
+                old_dir = make_data_tables.DATA_DIR
+                make_data_tables.DATA_DIR = tmp
+                try:
+                    t0 = time.perf_counter()
+                    make_data_tables.make_edit_distance(
+                        pal, make_data_tables.compute_substitute_costs(pal),
+                        screen.HGRBitmap, colours.HGRColours)
+                    dt = time.perf_counter() - t0
+                finally:
+                    make_data_tables.DATA_DIR = old_dir
+                path = os.path.join(tmp, "HGR_palette_%d_edit_distance.npz" % pal.ID.value)
+                line["npz_file"] = {
+                    "seconds": dt, "bytes": os.path.getsize(path),
+                    "host_threads": min(32, os.cpu_count() or 1),
+                    "note": "make_data_tables.make_edit_distance(HGR, NTSC) into a temporary "
+                            "directory: the file the reference's loader reads "
+                            "(np.load(...)['edit_distance'])"}
+        except Exception as e:   # noqa: BLE001
+            line["npz_file"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     if world == 1 and not args.no_scorer:

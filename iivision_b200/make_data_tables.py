@@ -7,7 +7,8 @@ colormath and weighted-levenshtein are not dependencies: the CIE2000 matrix is a
 FP64 device kernel (iiv_lut_cie2000) and the weighted Damerau-Levenshtein
 distances are the table kernels of csrc/iiv_tables.cu.  The reference's ~90
 CPU-minutes (README.md:64-67) become milliseconds of kernel time; what remains is
-the device->host copy and np.savez_compressed.
+the device->host copy and the compressed .npz write, whose deflate runs on all
+host cores (npz_io.py).
 """
 
 import functools
@@ -18,6 +19,7 @@ import numpy as np
 import torch
 
 from . import colours
+from . import npz_io
 from . import ops
 from . import palette
 from . import screen
@@ -176,7 +178,8 @@ def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,
     dist = compute_edit_distance(edp, bitmap_cls, nominal_colours)
     data = "%s/%s_palette_%d_edit_distance.npz" % (
         DATA_DIR, bitmap_cls.NAME, pal.ID.value)
-    np.savez_compressed(data, edit_distance=dist)
+    # same container and member as np.savez_compressed, deflated on all host cores
+    npz_io.savez_compressed(data, edit_distance=dist)
 
 
 def main():

@@ -1,0 +1,102 @@
+"""``np.savez_compressed`` with the deflate work spread over the host's cores.
+
+The reference stores each edit-distance table as a compressed ``.npz``
+(make_data_tables.py:186-188) and loads it back with ``np.load`` (screen.py:352).
+Once the table itself takes a quarter of a millisecond, zlib on one core (tens of
+seconds per GiB) is the whole cost of ``make_edit_distance``.  A deflate stream may be
+cut anywhere into independently compressed pieces as long as every piece but the last
+ends in a sync flush (byte-aligned, not final) -- the pigz construction -- so the pieces
+are compressed in a thread pool (zlib releases the GIL) and written in order into an
+ordinary ZIP container.  ``np.load`` and any unzip read the result like numpy's own.
+"""
+
+import os
+import struct
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+CHUNK = 8 << 20
+_LOCAL = b"PK\x03\x04"
+_CENTRAL = b"PK\x01\x02"
+_END = b"PK\x05\x06"
+_END64 = b"PK\x06\x06"
+_END64_LOC = b"PK\x06\x07"
+_DOS_DATE = (2019 - 1980) << 9 | 1 << 5 | 1     # fixed timestamp: files are reproducible
+
+
+def _npy_header(a: np.ndarray) -> bytes:
+    import io
+    buf = io.BytesIO()
+    np.lib.format.write_array_header_1_0(buf, np.lib.format.header_data_from_array_1_0(a))
+    return buf.getvalue()
+
+
+def _deflate_piece(args):
+    view, level, last = args
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    out = co.compress(view)
+    out += co.flush(zlib.Z_FINISH if last else zlib.Z_SYNC_FLUSH)
+    return out
+
+
+def _member(f, pool, name: str, a: np.ndarray, level: int):
+    """Writes one .npy member; returns its central-directory record fields."""
+    a = np.asarray(a, order="C")
+    if a.dtype.hasobject:
+        raise ValueError("object arrays are not supported")
+    header = _npy_header(a)
+    body = memoryview(a.reshape(-1).view(np.uint8)) if a.size else memoryview(b"")
+    pieces = [memoryview(header)]
+    pieces += [body[o:o + CHUNK] for o in range(0, len(body), CHUNK)]
+    jobs = [(p, level, k == len(pieces) - 1) for k, p in enumerate(pieces)]
+    raw_size = len(header) + len(body)
+    fname = (name + ".npy").encode("utf-8")
+    offset = f.tell()
+    # sizes and CRC are not known yet: ZIP64 extra field reserved, patched afterwards
+    extra = struct.pack("<HHQQ", 1, 16, 0, 0)
+    f.write(_LOCAL + struct.pack("<HHHHHIIIHH", 45, 0, 8, 0, _DOS_DATE, 0, 0xffffffff,
+                                 0xffffffff, len(fname), len(extra)) + fname + extra)
+    crc = 0
+    comp_size = 0
+    crc_done = 0
+    for k, out in enumerate(pool.map(_deflate_piece, jobs)):
+        f.write(out)
+        comp_size += len(out)
+        # the checksum runs over the raw bytes, piece by piece, while later pieces are
+        # still being compressed by the pool
+        crc = zlib.crc32(pieces[k], crc)
+        crc_done += len(pieces[k])
+    assert crc_done == raw_size
+    end = f.tell()
+    f.seek(offset + 14)
+    f.write(struct.pack("<I", crc))
+    f.seek(offset + 30 + len(fname) + 4)
+    f.write(struct.pack("<QQ", raw_size, comp_size))
+    f.seek(end)
+    return fname, crc, raw_size, comp_size, offset
+
+
+def savez_compressed(path, level: int = 6, threads: int = None, **arrays) -> None:
+    """Drop-in for ``np.savez_compressed(path, **arrays)`` (keyword form)."""
+    path = os.fspath(path)
+    if not path.endswith(".npz"):
+        path += ".npz"
+    threads = threads or min(32, os.cpu_count() or 1)
+    records = []
+    with open(path, "wb") as f, ThreadPoolExecutor(max_workers=threads) as pool:
+        for name, a in arrays.items():
+            records.append(_member(f, pool, name, np.asanyarray(a), level))
+        cd_start = f.tell()
+        for fname, crc, raw_size, comp_size, offset in records:
+            extra = struct.pack("<HHQQQ", 1, 24, raw_size, comp_size, offset)
+            f.write(_CENTRAL + struct.pack(
+                "<HHHHHHIIIHHHHHII", 45, 45, 0, 8, 0, _DOS_DATE, crc, 0xffffffff, 0xffffffff,
+                len(fname), len(extra), 0, 0, 0, 0, 0xffffffff) + fname + extra)
+        cd_size = f.tell() - cd_start
+        n = len(records)
+        f.write(_END64 + struct.pack("<QHHIIQQQQ", 44, 45, 45, 0, 0, n, n, cd_size, cd_start))
+        f.write(_END64_LOC + struct.pack("<IQI", 0, cd_start + cd_size, 1))
+        f.write(_END + struct.pack("<HHHHIIH", 0, 0, min(n, 0xffff), min(n, 0xffff),
+                                   0xffffffff, 0xffffffff, 0))
