@@ -8,6 +8,11 @@ cut anywhere into independently compressed pieces as long as every piece but the
 ends in a sync flush (byte-aligned, not final) -- the pigz construction -- so the pieces
 are compressed in a thread pool (zlib releases the GIL) and written in order into an
 ordinary ZIP container.  ``np.load`` and any unzip read the result like numpy's own.
+
+The writer also stores where its pieces start (member ``__deflate_pieces__``, which
+readers that ask for ``edit_distance`` never see), so that ``load_member`` can inflate
+them on all cores as well; files from ``np.savez_compressed`` itself are read through
+``np.load``.
 """
 
 import os
@@ -61,11 +66,13 @@ def _member(f, pool, name: str, a: np.ndarray, level: int):
     crc = 0
     comp_size = 0
     crc_done = 0
+    index = []          # (raw offset, raw length, file offset, compressed length, crc32)
     for k, out in enumerate(pool.map(_deflate_piece, jobs)):
+        index.append((crc_done, len(pieces[k]), f.tell(), len(out), zlib.crc32(pieces[k])))
         f.write(out)
         comp_size += len(out)
-        # the checksum runs over the raw bytes, piece by piece, while later pieces are
-        # still being compressed by the pool
+        # the member's checksum runs over the raw bytes, piece by piece, while later
+        # pieces are still being compressed by the pool
         crc = zlib.crc32(pieces[k], crc)
         crc_done += len(pieces[k])
     assert crc_done == raw_size
@@ -75,19 +82,35 @@ def _member(f, pool, name: str, a: np.ndarray, level: int):
     f.seek(offset + 30 + len(fname) + 4)
     f.write(struct.pack("<QQ", raw_size, comp_size))
     f.seek(end)
-    return fname, crc, raw_size, comp_size, offset
+    return (fname, crc, raw_size, comp_size, offset), index
 
 
-def savez_compressed(path, level: int = 6, threads: int = None, **arrays) -> None:
-    """Drop-in for ``np.savez_compressed(path, **arrays)`` (keyword form)."""
+PIECES = "__deflate_pieces__"
+
+
+def savez_compressed(path, level: int = 6, threads: int = None, index: bool = True,
+                     **arrays) -> None:
+    """Drop-in for ``np.savez_compressed(path, **arrays)`` (keyword form).  With
+    ``index`` an extra int64[n, 6] member lists (member number, raw offset, raw length,
+    file offset, compressed length, CRC-32 of the raw bytes) of every deflate piece for
+    ``load_member``."""
     path = os.fspath(path)
     if not path.endswith(".npz"):
         path += ".npz"
     threads = threads or min(32, os.cpu_count() or 1)
     records = []
     with open(path, "wb") as f, ThreadPoolExecutor(max_workers=threads) as pool:
-        for name, a in arrays.items():
-            records.append(_member(f, pool, name, np.asanyarray(a), level))
+        if PIECES in arrays:
+            raise ValueError("%s is a reserved member name" % PIECES)
+        table = []
+        for k, (name, a) in enumerate(arrays.items()):
+            rec, pieces = _member(f, pool, name, np.asanyarray(a), level)
+            records.append(rec)
+            table += [(k,) + p for p in pieces]
+        if index:
+            rec, _ = _member(f, pool, PIECES, np.array(table, dtype=np.int64).reshape(-1, 6),
+                             level)
+            records.append(rec)
         cd_start = f.tell()
         for fname, crc, raw_size, comp_size, offset in records:
             extra = struct.pack("<HHQQQ", 1, 24, raw_size, comp_size, offset)
@@ -100,3 +123,57 @@ def savez_compressed(path, level: int = 6, threads: int = None, **arrays) -> Non
         f.write(_END64_LOC + struct.pack("<IQI", 0, cd_start + cd_size, 1))
         f.write(_END + struct.pack("<HHHHIIH", 0, 0, min(n, 0xffff), min(n, 0xffff),
                                    0xffffffff, 0xffffffff, 0))
+
+
+def load_member(path, name: str, threads: int = None, alloc=None) -> np.ndarray:
+    """``np.load(path)[name]``.  Files written by ``savez_compressed`` above are inflated
+    piece by piece on ``threads`` cores, into the buffer ``alloc(n_bytes)`` returns (a
+    writable uint8 array, e.g. page-locked memory) when given; any other file goes through
+    ``np.load``."""
+    import io
+    import mmap
+    import zipfile
+    path = os.fspath(path)
+    with zipfile.ZipFile(path) as z:
+        names = z.namelist()
+        if name + ".npy" not in names:
+            raise KeyError("%s is not a file in the archive" % name)
+        if PIECES + ".npy" not in names:
+            with np.load(path) as npz:
+                return npz[name]
+        member = names.index(name + ".npy")
+        info = z.getinfo(name + ".npy")
+        with z.open(PIECES + ".npy") as fp:
+            table = np.lib.format.read_array(fp)
+    rows = table[table[:, 0] == member] if table.ndim == 2 and table.shape[1] == 6 else table[:0]
+    raw_size = int(info.file_size)
+    if (table.ndim != 2 or table.shape[1] != 6 or rows.size == 0
+            or int(rows[:, 2].sum()) != raw_size
+            or int(rows[:, 4].sum()) != int(info.compress_size)):
+        with np.load(path) as npz:       # index does not describe this member: plain path
+            return npz[name]
+    out = alloc(raw_size) if alloc is not None else np.empty(raw_size, dtype=np.uint8)
+    threads = threads or min(32, os.cpu_count() or 1)
+    with open(path, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+        view = memoryview(mm)
+
+        def inflate(row):
+            _, raw_off, raw_len, file_off, comp_len, crc = (int(x) for x in row)
+            data = zlib.decompressobj(-15).decompress(view[file_off:file_off + comp_len])
+            if len(data) != raw_len or zlib.crc32(data) != crc:
+                raise ValueError("corrupt deflate piece at file offset %d" % file_off)
+            out[raw_off:raw_off + raw_len] = np.frombuffer(data, dtype=np.uint8)
+
+        try:
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                list(pool.map(inflate, rows))
+        finally:
+            view.release()
+    head = io.BytesIO(out[:int(rows[0, 2])].tobytes())
+    version = np.lib.format.read_magic(head)
+    if version != (1, 0):
+        raise ValueError("unexpected .npy version %r" % (version,))
+    shape, fortran, dtype = np.lib.format.read_array_header_1_0(head)
+    body = out[head.tell():]
+    a = body.view(dtype)
+    return a.reshape(shape, order="F" if fortran else "C")

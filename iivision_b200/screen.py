@@ -30,6 +30,7 @@ from typing import List, Optional, Tuple, Union
 import numpy as np
 import torch
 
+from . import npz_io
 from . import ops
 from . import palette as pal
 
@@ -296,7 +297,11 @@ class Bitmap:
         """Symmetric uint16[n_offsets, 4**bits] table resident in HBM."""
         path = cls._table_path(palette_id)
         if os.path.exists(path):
-            tri = np.load(path)["edit_distance"]
+            # inflated on all host cores into page-locked memory when the file carries our
+            # writer's piece index, through np.load otherwise (npz_io.py)
+            tri = npz_io.load_member(
+                path, "edit_distance",
+                alloc=lambda n: torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy())
             want = ops.table_shape(cls.MODE)
             if tri.shape != want or tri.dtype != np.uint16:
                 raise ValueError("%s: expected uint16 %r" % (path, want))

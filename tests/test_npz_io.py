@@ -4,6 +4,7 @@ numpy's own (reference reader: screen.py:352, np.load(...)["edit_distance"])."""
 import importlib.util
 import os
 import zipfile
+import zlib
 
 import numpy as np
 import pytest
@@ -35,7 +36,7 @@ def test_round_trip_matches_numpy(tmp_path, threads):
     npz_io.savez_compressed(str(ours), threads=threads, **arrays)
     np.savez_compressed(str(theirs), **arrays)
     with np.load(str(ours)) as a, np.load(str(theirs)) as b:
-        assert sorted(a.files) == sorted(b.files)
+        assert sorted(set(a.files) - {npz_io.PIECES}) == sorted(b.files)
         for k in b.files:
             assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, k
             assert np.array_equal(a[k], b[k]), k
@@ -55,3 +56,45 @@ def test_suffix_is_added_and_pieces_are_cut_at_chunk_size(tmp_path, monkeypatch)
     npz_io.savez_compressed(str(tmp_path / "t"), edit_distance=data)
     with np.load(str(tmp_path / "t.npz")) as z:
         assert np.array_equal(z["edit_distance"], data)
+
+
+def test_load_member_parallel_and_fallback(tmp_path, monkeypatch):
+    npz_io = _load_module()
+    monkeypatch.setattr(npz_io, "CHUNK", 4096)
+    rng = np.random.default_rng(5)
+    arrays = {"edit_distance": rng.integers(0, 300, size=(4, 9001), dtype=np.uint16),
+              "f": np.asfortranarray(rng.integers(0, 9, size=(6, 5), dtype=np.int32)),
+              "empty": np.zeros((0,), np.uint8)}
+    ours, theirs = str(tmp_path / "ours.npz"), str(tmp_path / "theirs.npz")
+    npz_io.savez_compressed(ours, **arrays)
+    np.savez_compressed(theirs, **arrays)
+    handed_out = []
+
+    def alloc(n):
+        handed_out.append(np.empty(n, np.uint8))
+        return handed_out[-1]
+    for path in (ours, theirs):
+        for k, want in arrays.items():
+            got = npz_io.load_member(path, k, threads=3, alloc=alloc)
+            assert got.dtype == want.dtype and got.shape == want.shape, (path, k)
+            assert np.array_equal(got, want), (path, k)
+    assert len(handed_out) == 3           # the indexed file only; numpy's went through np.load
+    with np.load(ours) as z:              # the reference's reader sees the member it asks for
+        assert np.array_equal(z["edit_distance"], arrays["edit_distance"])
+    with pytest.raises(KeyError):
+        npz_io.load_member(ours, "missing")
+    # a damaged piece is reported, not returned
+    blob = bytearray(open(ours, "rb").read())
+    with zipfile.ZipFile(ours) as z:
+        start = z.getinfo("edit_distance.npy").header_offset
+    blob[start + 400] ^= 0xff
+    bad = str(tmp_path / "bad.npz")
+    open(bad, "wb").write(bytes(blob))
+    with pytest.raises((ValueError, zlib.error)):
+        npz_io.load_member(bad, "edit_distance")
+
+
+def test_reserved_member_name(tmp_path):
+    npz_io = _load_module()
+    with pytest.raises(ValueError):
+        npz_io.savez_compressed(str(tmp_path / "x.npz"), **{npz_io.PIECES: np.zeros(1)})
