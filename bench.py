@@ -707,7 +707,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3, done),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u16",
         "data": "synthetic (palette constants; no external data)",
         "config": dict(workload_config(world, exchange),
                        **({"exchange_note": exchange_note} if exchange_note else {})),
