@@ -21,6 +21,9 @@ The reference cannot travel to the GPU box, so its outputs do, as fixtures:
                        _double_pixels outputs of the reference classes
   byte_stream.npz      Movie.emit_stream bytes for synthetic tick opcodes + the opcode
                        address table of player/iivision.dbg
+  movie_<case>.npz     the byte stream of the whole Movie.encode + Movie.emit_stream loop
+                       (movie.py:56-161) on synthetic frames and audio ticks, with the
+                       final encoder state
   luts.json            int(dE2000) substitution matrices from oracle/cie2000.py
                        (restated colormath; NOT reference output -- the reference
                        generator cannot run offline) together with the rows
@@ -261,6 +264,83 @@ def gen_stream(ns, case, table):
     print("  %s: %d opcodes, %d real" % (name, len(ops), int(np.sum(real))))
 
 
+MOVIE_CASES = [
+    # name, mode, grabber frames, frame fraction, frame seed, rng seed, input fps, every_n,
+    # audio ticks, max_bytes_out
+    ("dhgr_30fps", "DHGR", 5, 1.0, 31, 3, 30, 2, 2300, None),
+    ("dhgr_24fps_capped", "DHGR", 4, 0.3, 32, 4, 24, 1, 2600, 9000),
+    ("hgr_30fps", "HGR", 4, 1.0, 33, 5, 30, 2, 1700, None),
+    ("hgr_frames_run_out", "HGR", 2, 0.2, 34, 6, 25, 1, 2000, None),
+]
+
+
+def gen_movie(ns, case, table):
+    """The whole of Movie.encode + Movie.emit_stream (movie.py:56-161) of the unmodified
+    reference, with the two media front ends replaced by in-memory sources: an audio
+    object giving sample_rate and audio_stream() (values -15..16, audio.py:84-103) and a
+    frame grabber giving input_frame_rate and frames() -> (main, aux) MemoryMaps
+    (frame_grabber.py:56-140).  Movie.__init__ would open the media file, so the object is
+    built field by field as its __init__ does (movie.py:16-54)."""
+    import contextlib
+    import io
+    name, mode, n_frames, fraction, fseed, seed, fps, every_n, n_ticks, max_out = case
+    ref_harness.install_tables(ns, mode, {5: table})
+    frames = synth.synthetic_frames(mode, n_frames, fraction, seed=fseed)
+    audio = np.random.default_rng(fseed).integers(-15, 17, size=n_ticks).astype(np.int8)
+    vm = getattr(ns.video_mode.VideoMode, mode)
+
+    class Audio:
+        sample_rate = 14700.
+
+        @staticmethod
+        def audio_stream():
+            yield from (int(a) for a in audio)
+
+    class Grabber:
+        input_frame_rate = fps
+
+        @staticmethod
+        def frames():
+            for k in range(n_frames):
+                main = ns.screen.MemoryMap(screen_page=1, page_offset=frames[k, 0].copy())
+                aux = (ns.screen.MemoryMap(screen_page=1, page_offset=frames[k, 1].copy())
+                       if mode == "DHGR" else None)
+                yield main, aux
+
+    random.seed(seed)
+    np.random.seed(seed)
+    m = ns.movie.Movie.__new__(ns.movie.Movie)
+    m.filename = "synthetic"
+    m.every_n_video_frames = every_n
+    m.max_bytes_out = max_out
+    m.video_mode = vm
+    m.palette = ns.palette.Palette.NTSC
+    m.audio = Audio()
+    m.frame_grabber = Grabber()
+    m.video = ns.video.Video(m.frame_grabber, ticks_per_second=m.audio.sample_rate,
+                             mode=vm, palette=m.palette)
+    m.stream_pos = 0
+    m.ticks = 0
+    m.state = ns.machine.Machine()
+    m.aux_memory_bank = False
+    with contextlib.redirect_stdout(io.StringIO()):
+        data = bytes(m.emit_stream(m.encode()))
+    out = {
+        "mode": mode, "frames": frames, "audio": audio, "rng_seed": seed,
+        "input_frame_rate": np.float64(fps), "every_n_video_frames": every_n,
+        "sample_rate": np.float64(14700.), "max_bytes_out": np.int64(max_out or 0),
+        "bytes": np.frombuffer(data, np.uint8), "ticks_pulled": np.int64(m.ticks),
+        "packed": m.video.pixelmap.packed.copy(),
+        "main": m.video.memory_map.page_offset.copy(),
+        "priority_main": m.video.update_priority.copy(),
+    }
+    if mode == "DHGR":
+        out["aux"] = m.video.aux_memory_map.page_offset.copy()
+        out["priority_aux"] = m.video.aux_update_priority.copy()
+    np.savez_compressed(os.path.join(GOLDEN, "movie_%s.npz" % name), **out)
+    print("  %s: %d bytes, %d ticks" % (name, len(data), m.ticks))
+
+
 def gen_luts():
     survey_row0 = {
         "5": [0, 35, 37, 50, 38, 39, 55, 64, 31, 53, 39, 65, 66, 78, 86, 99],
@@ -286,6 +366,13 @@ def main():
     print("byte stream"); gen_byte_stream(ns)
     if "--helpers-only" in sys.argv:
         return
+    if "--movie-only" in sys.argv:
+        for mode in ("HGR", "DHGR"):
+            table = symmetric_table(mode)
+            for case in MOVIE_CASES:
+                if case[1] == mode:
+                    gen_movie(ns, case, table)
+        return
     print("pixel strings"); gen_pixel_strings(ns)
     print("luts"); gen_luts()
     for mode in ("HGR", "DHGR"):
@@ -294,6 +381,9 @@ def main():
         for case in STREAM_CASES:
             if case[1] == mode:
                 gen_stream(ns, case, table)
+        for case in MOVIE_CASES:
+            if case[1] == mode:
+                gen_movie(ns, case, table)
 
 
 if __name__ == "__main__":

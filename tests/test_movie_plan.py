@@ -1,0 +1,74 @@
+"""CPU: the host-side schedule of a whole movie (movie.plan_movie) against what the
+unmodified reference's Movie.encode + Movie.emit_stream did on the same inputs
+(tests/golden/movie_*.npz, generator oracle/make_golden.py)."""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLDEN, "movie_*.npz")))
+
+
+@pytest.fixture(scope="module")
+def movie():
+    from iivision_b200 import _build
+    _build.build()
+    from iivision_b200 import movie
+    return movie
+
+
+def _plan(movie, g):
+    return movie.plan_movie(str(g["mode"]), len(g["audio"]), g["frames"].shape[0],
+                            float(g["sample_rate"]), float(g["input_frame_rate"]),
+                            int(g["every_n_video_frames"]), int(g["max_bytes_out"]) or None)
+
+
+def test_cases_present():
+    assert len(CASES) >= 4
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_plan_matches_reference_run(movie, case):
+    from iivision_b200._lib import lib
+    g = np.load(os.path.join(GOLDEN, "movie_%s.npz" % case))
+    plan = _plan(movie, g)
+    data = g["bytes"]
+    # stream length: header + emitted tick opcodes + Acks + Terminate + padding
+    assert int(lib.iiv_stream_length(plan.emitted, 1)) == len(data)
+    assert sum(s[2] for s in plan.segments) == plan.pulled
+    assert plan.emitted in (plan.pulled, plan.pulled - 1)
+    # Movie.ticks counts the tick whose frame could not be grabbed as well
+    assert int(g["ticks_pulled"]) in (plan.pulled, plan.pulled + 1)
+    # the speaker ticks sit in the opcode addresses; check the bank the Acks select instead:
+    # every 2 KiB frame ends in (ack address, $54 | aux, $ff), the bank alternating in DHGR
+    acks = [int(data[k * 2048 + 2046]) for k in range(len(data) // 2048 - 1)]
+    if str(g["mode"]) == "DHGR":
+        assert acks == [0x55 if k % 2 == 0 else 0x54 for k in range(len(acks))]
+    else:
+        assert set(acks) <= {0x54}
+    # generators: new frame or bank flip, never empty, banks as the Acks left them
+    for (slot, is_aux, count) in plan.segments:
+        assert count > 0 and 0 <= slot < len(plan.frames_used)
+        assert is_aux in (0, 1) and (str(g["mode"]) == "DHGR" or is_aux == 0)
+    every = int(g["every_n_video_frames"])
+    assert plan.frames_used == list(range(0, g["frames"].shape[0], every))[:len(plan.frames_used)]
+
+
+def test_plan_degenerate_inputs(movie):
+    assert movie.plan_movie("DHGR", 0, 3).pulled == 0
+    assert movie.plan_movie("HGR", 100, 0) == movie.MoviePlan([], [], 0, 0)
+    p = movie.plan_movie("DHGR", 1000, 1, 14700., 30., 1, None)
+    # a single frame: its successor is due at tick 490 and cannot be grabbed
+    assert p.pulled == 489 and p.frames_used == [0]
+    assert p.segments == [(0, 0, 291), (0, 1, 198)]
+    # max_bytes_out below the header: the first opcode is computed and dropped
+    q = movie.plan_movie("HGR", 50, 1, max_bytes_out=5)
+    assert (q.pulled, q.emitted) == (1, 0)
+
+
+def test_movie_needs_media_sources(movie):
+    with pytest.raises(NotImplementedError):
+        movie.Movie("clip.mp4")
