@@ -343,6 +343,10 @@ def scorer_figures(torch, ops, single=True):
         out.update(facade_figures(torch))
     except Exception as e:   # noqa: BLE001
         out["facade_error"] = repr(e)
+    try:
+        out.update(movie_figures(torch, ops, table))
+    except Exception as e:   # noqa: BLE001
+        out["movie_error"] = repr(e)
     ms1, all1, trace1 = encode_run(1, 16)
     out["single_clip_trace"] = trace1
     out["single_clip_frames_per_s"] = 16 / (ms1 * 1e-3)
@@ -409,6 +413,52 @@ def facade_figures(torch, n_frames=8):
             "facade_note": ("video.Video.encode_frame under the Movie.encode schedule, %d DHGR "
                             "frames after one warm-up frame, %d generators, host arrays in and "
                             "out; wall clock" % (n_frames, sum(1 for s_ in segs if s_[0] > 0)))}
+
+
+def movie_figures(torch, ops, table, n_encoded=16):
+    """A whole DHGR movie -- frames and audio samples on the host in, .a2m bytes on the host
+    out -- through movie.transcode_device: schedule on the host, one encoder launch, one
+    byte-layout launch (30 fps input, every second frame encoded, 14 700 ticks/s as
+    main.py's defaults)."""
+    import random
+    import numpy as np
+    from iivision_b200 import movie, opcodes, synth
+    n_grabbed = 2 * n_encoded
+    frames = synth.synthetic_frames("DHGR", n_grabbed, 1.0, seed=200)
+    samples = np.random.default_rng(200).integers(-15, 17, size=490 * n_grabbed - 1)
+    try:
+        addresses = opcodes.address_table()
+    except ValueError:          # no player/iivision.dbg here: any address table times the same
+        addresses = (np.arange(1024, dtype=np.uint16).reshape(32, 32) + 0x8000, 0x7f00, 0x7f80)
+    pad = np.zeros(640, np.uint32)
+    times = []
+    n_bytes = 0
+    for rep in range(4):
+        st = ops.new_clip_states(1)
+        pad[:625] = ops.mt_from_python(random.Random(0).getstate())
+        ops.state_field(st, ops.F_MT_PY, torch.int32, (640,)).copy_(
+            torch.from_numpy(pad.view(np.int32)).cuda().expand(1, 640))
+        pad[:625] = ops.mt_from_numpy(np.random.RandomState(0).get_state())
+        ops.state_field(st, ops.F_MT_NP, torch.int32, (640,)).copy_(
+            torch.from_numpy(pad.view(np.int32)).cuda().expand(1, 640))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        data, plan = movie.transcode_device("DHGR", frames, samples, table, st,
+                                            every_n_video_frames=2, addresses=addresses)
+        host = data.cpu()
+        dt = time.perf_counter() - t0
+        n_bytes = host.numel()
+        if rep:
+            times.append(dt)
+    times.sort()
+    dt = times[len(times) // 2]
+    return {"movie_frames_per_s": len(plan.frames_used) / dt,
+            "movie_stream_bytes": n_bytes,
+            "movie_note": ("movie.transcode_device: %d grabbed DHGR frames (%d encoded), %d "
+                           "audio ticks = %.1f s of playback, host arrays in, .a2m bytes on the "
+                           "host out; wall clock, median of %d" % (
+                               n_grabbed, len(plan.frames_used), plan.emitted,
+                               plan.emitted / 14700., len(times)))}
 
 
 def hgr_clip_and_cpu(torch, ops, table_dhgr):
