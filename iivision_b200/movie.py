@@ -261,9 +261,11 @@ def emit_stream_device(mode, opcode_records: torch.Tensor, ticks: torch.Tensor,
 
 def stream_schedule(mode: str, n_frames: int, opcodes_per_frame: int = 980
                     ) -> List[Tuple[int, int, int]]:
-    """(frame, is_aux, budget) segments as Movie.encode + emit_stream produce them: a new
-    encode_frame per encoded frame and, in DHGR, per bank flip -- after 291 tick opcodes
-    in the first 2 KiB frame (7 header bytes), every 292 afterwards."""
+    """Fixed-rate (frame, is_aux, budget) segments for synthetic workloads: exactly
+    ``opcodes_per_frame`` pulls per frame and, in DHGR, a new generator per bank flip -- after
+    291 tick opcodes in the first 2 KiB frame (7 header bytes), every 292 afterwards.
+    ``plan_movie`` is the real thing (there the first frame is one tick short, because tick
+    numbering starts at 1 while frame k is due at tick k * ticks_per_frame)."""
     segs = []
     aux = False
     count = 0
