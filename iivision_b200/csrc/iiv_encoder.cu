@@ -91,11 +91,19 @@ struct Smem {
   // delta is one of the two smallest -- only they can be among the two winners, whatever
   // the nonces turn out to be.  (delta + 32768) << 16 | nonce rank << 8 | offset.
   uint32_t rec_cont[kRecRing][32];
-  // entry, cell | content << 16, n_cand | n_contenders << 16, b_done seen
-  alignas(16) uint32_t rec_hdr[kRecRing][4];
-  uint32_t rec_tag[kRecRing];                    // record number the slot holds
-  volatile int pop_turn;          // next record number to be popped
-  volatile int pop_cursor;        // sorted-heap cursor of that pop
+  // One 16-byte word per record, written with a single store and polled with a single
+  // load, so that it is its own "ready" flag (no flag/data ordering to get wrong):
+  //   x = entry | kind << 14 | ((record number + 1) & 0xffff) << 16
+  //   y = cell | content << 13 | n_cand << 21            (bits 30, 31 are zero)
+  //   z = o1 | o2 << 8 | min(n_contenders, 63) << 16 | (r - b_done seen) << 22
+  //       | settled << 26 | has1 << 27 | has2 << 28
+  //   w = new diff at o1 | new diff at o2 << 16
+  // settled: the winners do not depend on the nonces and the front end has already looked
+  // them up (o1/o2/has1/has2/w); otherwise the contenders are in rec_cont.
+  alignas(16) uint32_t rec[kRecRing][4];
+  // (next record number to be popped) << 14 | sorted-heap cursor of that pop: one word, so
+  // that turn and cursor cannot be seen out of step
+  volatile uint32_t pop_state;
   volatile int b_done;            // records the decision warp has finished with
   volatile int final_emitted;     // total records of the segment (set before stop)
   volatile int applied_pub;       // records applied so far
@@ -166,11 +174,13 @@ __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
   __syncwarp();
 }
 
-// 16-byte shared-memory load that the compiler neither caches nor moves (data that
-// another warp publishes behind a flag).
+// 16-byte volatile shared-memory load (CUDA C++ has no volatile vector loads): data that
+// another warp publishes.  Being volatile in PTX as well, ptxas keeps it where it is -- a
+// plain ld.shared in an asm statement is fair game for hoisting above a spin loop, however
+// the statement is decorated.
 __device__ __forceinline__ uint4 lds_v4(const void* p) {
   uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "r"((uint32_t)__cvta_generic_to_shared(p))
                : "memory");
@@ -664,12 +674,12 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     // with nanosleep.
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr int kDecideWarp = 7, kTwistWarp = 3, kApplyWarp = 4;
-    constexpr uint32_t kEndOfHeap = 0xffffffffu, kDeadRecord = 0xffffffffu;
+    constexpr uint32_t kKindLive = 0u, kKindDead = 1u, kKindEndOfHeap = 2u;
     if (t < kRing) {
       sm.ring_tag[t] = 0xffffffffu;
       sm.ring_claim[t] = 0;
     }
-    if (t < kRecRing) sm.rec_tag[t] = 0xffffffffu;
+    if (t < kRecRing) *reinterpret_cast<uint4*>(sm.rec[t]) = make_uint4(0u, 0u, 0u, 0u);
     if (t == 0) {
       sm.head = 0;
       sm.stop = 0;
@@ -678,8 +688,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       sm.np_pre = 0;
       sm.final_emitted = 0;
       sm.applied_pub = 0;
-      sm.pop_turn = 0;
-      sm.pop_cursor = 0;
+      sm.pop_state = 0u;
       sm.b_done = 0;
     }
     if (t < kOpQueue) sm.opq[t] = 0ull;
@@ -690,7 +699,6 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     const long long clk_b = clock64();
     long long wait_rows = 0, wait_misc = 0, wait_mt = 0;   // decision-warp stall cycles (diagnostics)
     volatile uint32_t* tags = sm.ring_tag;
-    volatile uint32_t* rtags = sm.rec_tag;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     // Candidate analysis of the 8 offsets a lane owns on `page` for the entry at
@@ -762,7 +770,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           // the refill asked for one block ago must be in before its buffer can be read
           if (mt_seen < mt_issued) {
             const long long c0 = clock64();
-            while (mt_seen < mt_issued) mt_seen = sm.mt_done;
+            // the twister shares this warp's scheduler: sleep rather than spin, or the
+            // poll starves the very warp it is waiting for
+            while ((mt_seen = sm.mt_done) < mt_issued) __nanosleep(40);
+            __threadfence_block();    // the block's nonce bytes are read after the flag
             wait_mt += clock64() - c0;
           }
           py_cur = py_cur == 2 ? 0 : py_cur + 1;
@@ -779,39 +790,50 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
 
         int cell, slot, rank, n_cand, n_cont = -1;   // n_cont < 0: evaluate all 256 offsets
         uint32_t content, m8, e8, khi[8], cont = 0;
+        uint32_t settled = 0, settled_p = 0;         // words z, w of a front-end record
         bool have = false;
         if (!heap_done) {
           // ---- next record of the front ends -------------------------------------------
           const int rs = r % kRecRing;
-          if (rtags[rs] != (uint32_t)r) {
+          const uint32_t seq = (uint32_t)(r + 1) & 0xffffu;
+          uint4 rec = lds_v4(sm.rec[rs]);
+          if ((rec.x >> 16) != seq) {
             const long long c0 = clock64();
-            while (rtags[rs] != (uint32_t)r) {}
+            do {
+              rec = lds_v4(sm.rec[rs]);
+            } while ((rec.x >> 16) != seq);
             wait_rows += clock64() - c0;
           }
-          asm volatile("" ::: "memory");
-          const uint4 hdr = lds_v4(sm.rec_hdr[rs]);
-          if (hdr.x == kEndOfHeap) {
+          const uint32_t kind = (rec.x >> 14) & 3u;
+          if (kind == kKindEndOfHeap) {
             heap_done = true;
             if (lane == 0) sm.head = n_first;
           } else {
-            const int e = (int)hdr.x;
-            cell = (int)(hdr.y & 0xffffu);
-            content = hdr.y >> 16;
+            const int e = (int)(rec.x & 0x3fffu);
+            cell = (int)(rec.y & 0x1fffu);
+            content = (rec.y >> 13) & 0xffu;
             slot = e % kRing;
             if (lane == 0) sm.head = e;
             // valid unless a record decided after the front end's read hit this page
-            const int seen = (int)hdr.w;
-            const bool in_window = (lane < 16) & (((r - 1 - lane) & 15) < r - seen);
+            const int since = (int)((rec.z >> 22) & 15u);     // records decided since then
+            const bool in_window = (lane < 16) & (((r - 1 - lane) & 15) < since);
             const bool conflict =
                 __ballot_sync(kFull, in_window && hist == (uint32_t)(cell >> 8)) != 0;
-            if (hdr.w == kDeadRecord) {
+            const uint32_t n_cont_rec = (rec.z >> 16) & 63u;
+            if (kind == kKindDead) {
               // dropped by the front end: the cell is zero
-            } else if (!conflict && (hdr.z >> 16) <= 32u) {
-              n_cand = (int)(hdr.z & 0xffffu);
-              n_cont = (int)(hdr.z >> 16);
-              cont = reinterpret_cast<volatile uint32_t*>(sm.rec_cont[rs])[lane];
+            } else if (!conflict && n_cont_rec <= 32u) {
+              n_cand = (int)((rec.y >> 21) & 0x1ffu);
+              n_cont = (int)n_cont_rec;
+              settled = rec.z;
+              settled_p = rec.w;
+              // the contenders were stored before the record word; the address depends on
+              // the word just loaded (its two top bits are zero), which pins the order of
+              // the two loads whatever the optimisers think of volatile
+              if (!((settled >> 26) & 1u))
+                cont = reinterpret_cast<volatile uint32_t*>(sm.rec_cont[rs] + (rec.y >> 30))[lane];
               have = true;
-            } else if (sm.prio[cell] != 0) {
+            } else if (reinterpret_cast<volatile int32_t*>(sm.prio)[cell] != 0) {
               digest(cell, sm.ring_row[slot], khi, m8, e8, rank, n_cand);
               have = true;
             }
@@ -865,6 +887,23 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         // only those with a live priority compete (:159); the two smallest (delta, nonce,
         // offset) win
         uint32_t b1, b2;
+        uint32_t p1 = 0, p2 = 0;
+        int o1 = off, o2 = off;
+        bool has1, has2;
+        if ((settled >> 26) & 1u) {
+          // the two smallest deltas are unique: no nonce can change the winners, and the
+          // front end has already looked up their new diffs
+          has1 = (settled >> 27) & 1u;
+          has2 = (settled >> 28) & 1u;
+          if (has1) {
+            o1 = (int)(settled & 255u);
+            p1 = settled_p & 0xffffu;
+          }
+          if (has2) {
+            o2 = (int)((settled >> 8) & 255u);
+            p2 = settled_p >> 16;
+          }
+        } else {
         if (n_cont >= 0) {
           // front-end record: lane i holds contender i
           uint32_t key = 0xffffffffu;
@@ -898,22 +937,25 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           b2 = __reduce_min_sync(kFull, best1 == b1 ? best2 : best1);
         }
         // byte_pair_difference of the accepted offsets (video.py:166) = their new diff
-        uint32_t p1 = 0, p2 = 0;
-        int o1 = off, o2 = off;
-        if (b1 != 0xffffffffu) {
+        has1 = b1 != 0xffffffffu;
+        has2 = b2 != 0xffffffffu;
+        if (has1) {
           o1 = (int)(b1 & 255u);
           p1 = sm.ring_row[slot][o1];
         }
-        if (b2 != 0xffffffffu) {
+        if (has2) {
           o2 = (int)(b2 & 255u);
           p2 = sm.ring_row[slot][o2];
         }
+        }
         const int push1 = p1 != 0, push2 = p2 != 0;
         if (lane == 0) {
-          sm.prio[cell] = 0;   // video.py:140
-          sm.dw[cell] = 0;     // video.py:141
-          if (b1 != 0xffffffffu) sm.prio[page * 256 + o1] = (int32_t)p1;   // video.py:170
-          if (b2 != 0xffffffffu) sm.prio[page * 256 + o2] = (int32_t)p2;
+          // volatile: these stores must stay ahead of the b_done store below
+          volatile int32_t* vprio = sm.prio;
+          vprio[cell] = 0;                                             // video.py:140
+          reinterpret_cast<volatile uint16_t*>(sm.dw)[cell] = 0;      // video.py:141
+          if (has1) vprio[page * 256 + o1] = (int32_t)p1;            // video.py:170
+          if (has2) vprio[page * 256 + o2] = (int32_t)p2;
           if (push1)   // video.py:173-178
             sm.pushed[n_pushed] = requeue_key(p1, push_nonce0, page * 256 + o1);
           if (push2)
@@ -968,33 +1010,32 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       for (int r = f;; r += kFronts) {
         // my turn to pop, with room in the record ring?
         bool quit = false;
+        uint32_t pop = 0;
         while (true) {
           if (sm.stop) {
             quit = true;
             break;
           }
-          if (sm.pop_turn == r && r < sm.b_done + kRecRing) break;
+          pop = sm.pop_state;
+          if ((int)(pop >> 14) == r && r < sm.b_done + kRecRing) break;
           __nanosleep(20);
         }
         if (quit) break;
         const int rs = r % kRecRing;
-        const int e = probe(sm.pop_cursor);
+        const uint32_t seq = ((uint32_t)(r + 1) & 0xffffu) << 16;
+        const int e = probe((int)(pop & 0x3fffu));
         if (e < 0) {
           // heap exhausted: tell the decision warp, and let the other front end see it too
           if (lane == 0) {
-            sm.rec_hdr[rs][0] = kEndOfHeap;
-            __threadfence_block();
-            rtags[rs] = (uint32_t)r;
-            sm.pop_turn = r + 1;
+            *reinterpret_cast<uint4*>(sm.rec[rs]) =
+                make_uint4(seq | (kKindEndOfHeap << 14), 0u, 0u, 0u);
+            sm.pop_state = ((uint32_t)(r + 1) << 14) | (pop & 0x3fffu);
           }
           break;
         }
         const int cell = (int)(sm.keys[e] & 0x1fffu);
-        const int seen = sm.b_done;      // BEFORE the page is read
-        if (lane == 0) {
-          sm.pop_cursor = e + 1;
-          sm.pop_turn = r + 1;
-        }
+        const int seen = sm.b_done;      // BEFORE the page is read (fence below)
+        if (lane == 0) sm.pop_state = ((uint32_t)(r + 1) << 14) | (uint32_t)(e + 1);
         // the row of this entry, from the producers.  If the cell has been zeroed since the
         // probe (by an opcode decided meanwhile) nobody may ever score it: hand over a
         // dead record, which the decision warp drops like the pop-and-skip it stands for.
@@ -1020,15 +1061,14 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         }
         if (quit) break;
         if (dead) {
-          if (lane == 0) {
-            *reinterpret_cast<uint4*>(sm.rec_hdr[rs]) =
-                make_uint4((uint32_t)e, (uint32_t)cell, 0u, kDeadRecord);
-            __threadfence_block();
-            rtags[rs] = (uint32_t)r;
-          }
+          if (lane == 0)
+            *reinterpret_cast<uint4*>(sm.rec[rs]) = make_uint4(
+                seq | (kKindDead << 14) | (uint32_t)e, (uint32_t)cell, 0u, 0u);
           continue;
         }
-        asm volatile("" ::: "memory");
+        // The row (after its tag) and the page (after `seen`) are read behind a fence: this
+        // warp is off the opcode chain, so ordering is bought, not argued.
+        __threadfence_block();
         uint32_t khi[8], m8, e8;
         int rank, n_cand;
         digest(cell, sm.ring_row[slot], khi, m8, e8, rank, n_cand);
@@ -1050,14 +1090,43 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         for (int j = 0; j < 8; ++j)
           if (((use8 >> j) & 1u) && khi[j] <= d2) c8 |= 1u << j;
         const int mine = __popc(c8);
-        int incl = mine;
+        const int n_cont = (int)__reduce_add_sync(kFull, (uint32_t)mine);
+        // With at most one candidate at each of the two smallest deltas the nonces cannot
+        // change the outcome (video.py:295-301 sorts by delta first): settle the winners and
+        // their new diffs here, off the decision warp's chain.  Otherwise hand over the
+        // contenders with their nonce ranks.
+        uint32_t settled = 0, settled_p = 0;
+        if (n_cont <= 1 || (n_cont == 2 && d2 != 0xffffffffu)) {
+          uint32_t mine_key = 0xffffffffu;     // a lane holds both winners only if c8 has 2 bits
+          uint32_t mine_key2 = 0xffffffffu;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(kFull, incl, d);
-          if (lane >= d) incl += v;
-        }
-        const int n_cont = __shfl_sync(kFull, incl, 31);
-        if (n_cont <= 32) {
+          for (int j = 0; j < 8; ++j) {
+            if ((c8 >> j) & 1u) {
+              const uint32_t k = (khi[j] << 16) | (uint32_t)(8 * lane + j);
+              mine_key2 = min(mine_key2, max(mine_key, k));
+              mine_key = min(mine_key, k);
+            }
+          }
+          const uint32_t k1 = __reduce_min_sync(kFull, mine_key);
+          const uint32_t k2 = __reduce_min_sync(kFull, mine_key == k1 ? mine_key2 : mine_key);
+          settled = 1u << 26;
+          if (k1 != 0xffffffffu) {
+            const uint32_t w1 = k1 & 255u;
+            settled |= w1 | (1u << 27);
+            settled_p = sm.ring_row[slot][w1];
+          }
+          if (k2 != 0xffffffffu) {
+            const uint32_t w2 = k2 & 255u;
+            settled |= (w2 << 8) | (1u << 28);
+            settled_p |= (uint32_t)sm.ring_row[slot][w2] << 16;
+          }
+        } else if (n_cont <= 32) {
+          int incl = mine;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += v;
+          }
           int at = incl - mine;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -1067,14 +1136,15 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             }
           }
         }
-        if (lane == 0)
-          *reinterpret_cast<uint4*>(sm.rec_hdr[rs]) = make_uint4(
-              (uint32_t)e, (uint32_t)cell | ((tag & 0xffu) << 16),
-              (uint32_t)n_cand | ((uint32_t)min(n_cont, 0xffff) << 16), (uint32_t)seen);
+        // the contenders (all lanes) go first, then the record word
         __syncwarp();
         if (lane == 0) {
           __threadfence_block();
-          rtags[rs] = (uint32_t)r;
+          *reinterpret_cast<uint4*>(sm.rec[rs]) = make_uint4(
+              seq | (kKindLive << 14) | (uint32_t)e,
+              (uint32_t)cell | ((tag & 0xffu) << 13) | ((uint32_t)n_cand << 21),
+              settled | ((uint32_t)min(n_cont, 63) << 16) | ((uint32_t)(r - seen) << 22),
+              settled_p);
         }
       }
     } else if (warp < kProducers) {
@@ -1130,7 +1200,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             reinterpret_cast<uint4*>(sm.ring_row[slot])[lane] = which ? row1 : row0;
             __syncwarp();
             if (lane == 0) {
-              // after __syncwarp: every lane's row stores are ordered before the tag
+              // after __syncwarp + fence: every lane's row stores are ordered before the tag
+              __threadfence_block();
               reinterpret_cast<volatile uint32_t*>(sm.ring_claim)[slot] = (uint32_t)e + 1u;
               tags[slot] = ((uint32_t)e << 8) | (which ? c1 : c0);
             }
