@@ -43,6 +43,7 @@ constexpr int kFronts = 2;               // front-end warps of the opcode loop
 constexpr int kRecRing = 8;              // popped entries digested ahead of the decision warp
 constexpr int kOpQueue = 64;            // emitted opcodes waiting for their stores
 constexpr int kRing = 16;               // prefetched delta rows in flight
+constexpr int kPyBlocks = 4;            // resident 624-word blocks of stream P (power of 2)
 constexpr int kCells = 32 * 256;       // one bank: 32 pages x 256 offsets
 constexpr int kCols = 32 * 128;
 constexpr int kPushedCap = 4096;       // >= 2 * max budget per segment
@@ -67,7 +68,7 @@ struct Smem {
   int32_t prio[kCells];        // update_priority of the active bank
   uint16_t dw[kCells];         // local diff_weights (video.py:109-111)
   uint32_t mt_np[2][624];      // stream N, ping-pong
-  uint32_t mt_py[3][624];      // stream P: current block and its two successors (ring)
+  uint32_t mt_py[kPyBlocks][624];   // stream P: current block and its successors (ring)
   uint64_t wmin64[8];
   int32_t scan[kThreads / 32];
   uint32_t hist[kThreads / 32][257];   // per-warp digit histograms of the heap select
@@ -80,10 +81,11 @@ struct Smem {
   uint32_t ring_tag[kRing];       // sorted-array index the slot holds
   uint32_t ring_claim[kRing];     // 1 + newest entry that has written (or is writing) the slot
   // top byte of the tempered words of stream P (= getrandbits(8), video.py:178, :291):
-  // slot s < 3 holds the block whose number is s (mod 3), slot 3 repeats slot 0, so that
-  // the bytes of the current block and of its successor are always contiguous
-  uint8_t py_nonce[4 * 624 + 16];
-  // emitted records waiting for warp 6 to apply their stores; byte 7 of a record
+  // slot s < kPyBlocks holds the block whose number is s (mod kPyBlocks), the last slot
+  // repeats slot 0, so that the bytes of the current block and of its successor are
+  // always contiguous
+  uint8_t py_nonce[(kPyBlocks + 1) * 624 + 16];
+  // emitted records waiting for the applier warp to apply their stores; byte 7 of a record
   // carries (sequence number & 255), so one 64-bit store publishes it
   unsigned long long opq[kOpQueue];
   // front-end records: a popped heap entry with its candidate analysis (see phase B)
@@ -110,7 +112,6 @@ struct Smem {
   volatile int head;              // heap entries the consumer is done with
   volatile int stop;              // segment finished: producers leave
   volatile int mt_req, mt_done;   // stream P block twists requested / finished
-  volatile int mt_src;            // buffer to twist from
   volatile int np_pre;            // successor blocks of stream N prepared during phase B
 };
 
@@ -128,13 +129,13 @@ __device__ __forceinline__ void twist(const uint32_t* __restrict__ s,
 
 // The same generation step done by a single warp (phase B helper warp).
 // Also stores getrandbits(8) = top byte of each tempered new word into the block's
-// slot(s) of py_nonce (slot s < 3 holds block numbers s mod 3; slot 3 repeats slot 0).
+// slot(s) of py_nonce (slot s holds block numbers s mod kPyBlocks; one more repeats slot 0).
 template <bool kNonces>
 __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
                                            uint32_t* __restrict__ d, int lane, int slot,
                                            uint8_t* __restrict__ py_nonce) {
   uint8_t* nb = py_nonce + slot * 624;
-  uint8_t* nb2 = py_nonce + (slot == 0 ? 3 * 624 : slot * 624);
+  uint8_t* nb2 = py_nonce + (slot == 0 ? kPyBlocks * 624 : slot * 624);
   // three dependent sweeps of 227 / 227 / 170 words; inside a sweep every word is
   // independent, so the loops are fully unrolled to keep 8 loads in flight per lane
 #pragma unroll
@@ -195,7 +196,7 @@ __device__ __forceinline__ void fill_nonces(const uint32_t* __restrict__ block, 
   for (int k = idx; k < 624; k += stride) {
     const uint8_t b = (uint8_t)(mt_temper(block[k]) >> 24);
     py_nonce[slot * 624 + k] = b;
-    if (slot == 0) py_nonce[3 * 624 + k] = b;
+    if (slot == 0) py_nonce[kPyBlocks * 624 + k] = b;
   }
 }
 
@@ -349,11 +350,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
   // whole block (~8 opcodes) before it can be needed.
   int py_cur = 0;                 // slot of the current block
   __syncthreads();
-  twist(sm.mt_py[0], sm.mt_py[1]);
-  twist(sm.mt_py[1], sm.mt_py[2]);
-  fill_nonces(sm.mt_py[0], 0, sm.py_nonce, t, kThreads);
-  fill_nonces(sm.mt_py[1], 1, sm.py_nonce, t, kThreads);
-  fill_nonces(sm.mt_py[2], 2, sm.py_nonce, t, kThreads);
+  for (int b = 1; b < kPyBlocks; ++b) twist(sm.mt_py[b - 1], sm.mt_py[b]);
+  for (int b = 0; b < kPyBlocks; ++b) fill_nonces(sm.mt_py[b], b, sm.py_nonce, t, kThreads);
   int error_flags = 0;
 
   uint8_t* op_out = opcodes + (size_t)clip * total_budget * 8;
@@ -763,28 +761,25 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       bool heap_done = false;    // sorted heap exhausted: re-queued cells only
       uint32_t hist = 0xffu;     // lane l < 16: page of the record r' = l (mod 16) decided last
       while (emitted < budget) {
-        // ---- stream P bookkeeping: three resident 624-word blocks ----------------------
-        // (every lane polls the same shared word in one broadcast load, so the loop
-        // conditions below are warp-uniform)
+        // ---- stream P bookkeeping: kPyBlocks resident 624-word blocks ------------------
+        // Moving on to block c frees the slot of block c - 1, into which the twister makes
+        // block c + 3 (request number = blocks left behind).  Reads run over into block
+        // c + 1 at most, which was requested two moves ago: one request may be outstanding.
+        // (Every lane polls the same shared word in one broadcast load, so the loop
+        // conditions below are warp-uniform.)
         if (pos_py > 624) {
-          // the refill asked for one block ago must be in before its buffer can be read
-          if (mt_seen < mt_issued) {
+          if (mt_seen < mt_issued - 1) {
             const long long c0 = clock64();
             // the twister shares this warp's scheduler: sleep rather than spin, or the
             // poll starves the very warp it is waiting for
-            while ((mt_seen = sm.mt_done) < mt_issued) __nanosleep(40);
+            while ((mt_seen = sm.mt_done) < mt_issued - 1) __nanosleep(40);
             __threadfence_block();    // the block's nonce bytes are read after the flag
             wait_mt += clock64() - c0;
           }
-          py_cur = py_cur == 2 ? 0 : py_cur + 1;
+          py_cur = (py_cur + 1) & (kPyBlocks - 1);
           pos_py -= 624;
           ++mt_issued;
-          if (lane == 0) {
-            // blocks cur, cur+1 are resident; cur+2 is made from cur+1 into the freed slot
-            sm.mt_src = py_cur == 2 ? 0 : py_cur + 1;
-            __threadfence_block();
-            sm.mt_req = mt_issued;
-          }
+          if (lane == 0) sm.mt_req = mt_issued;
         }
         const uint8_t* nonces = sm.py_nonce + py_cur * 624 + pos_py;
 
@@ -1286,9 +1281,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         req = __shfl_sync(kFull, req, 0);
         st = __shfl_sync(kFull, st, 0);
         if (req > done) {
-          __threadfence_block();
-          const int src = sm.mt_src;
-          const int dst = src == 2 ? 0 : src + 1;
+          // request n (from 1) replaces the block n behind the segment's first one by the
+          // block kPyBlocks - 1 + n ahead of it, made from its predecessor
+          const int dst = (py_cur + done) & (kPyBlocks - 1);
+          const int src = (dst + kPyBlocks - 1) & (kPyBlocks - 1);
           warp_twist<true>(sm.mt_py[src], sm.mt_py[dst], lane, dst, sm.py_nonce);
           ++done;
           __threadfence_block();
@@ -1361,7 +1357,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
 
   // ---- store persistent state ----------------------------------------------------
   if (pos_py > 624) {  // normalise so that (state, pos) is a legal MT19937 state
-    py_cur = py_cur == 2 ? 0 : py_cur + 1;
+    py_cur = (py_cur + 1) & (kPyBlocks - 1);
     pos_py -= 624;
   }
   for (int k = t; k < kCols; k += kThreads) g_packed[k] = sm.src[k];
