@@ -10,6 +10,8 @@
 // 0, native illuminant D65) -> Lab against the D65 2-degree white with
 // eps = 216/24389 and linear branch 7.787 t + 16/116 -> delta_e_cie2000 with
 // Kl = Kc = Kh = 1 in colormath's vectorised form.
+#include <mutex>
+
 #include "iiv_common.cuh"
 
 namespace iiv {
@@ -84,25 +86,29 @@ struct Rgb16 {
   uint8_t v[48];
 };
 
-__global__ void lut_kernel(Rgb16 rgb, double* de) {
+// Result buffer of the (host-in, host-out) matrix call: a module global, one per device,
+// so that the call neither allocates nor frees (cudaFree synchronises the whole device and
+// was seen to take 0.2 s right after a 1 GiB page-locked buffer had been set up).
+__device__ double g_delta_e[256];
+
+__global__ void lut_kernel(Rgb16 rgb) {
   const int i = threadIdx.x >> 4, j = threadIdx.x & 15;
   double la[3], lb[3];
   srgb_to_lab(rgb.v + 3 * i, la);
   srgb_to_lab(rgb.v + 3 * j, lb);
-  de[threadIdx.x] = delta_e_2000(la, lb);
+  g_delta_e[threadIdx.x] = delta_e_2000(la, lb);
 }
 
 int run(const uint8_t* h_rgb, double* h_de) {
   IIV_REQUIRE(h_rgb && h_de, "null pointer");
   Rgb16 rgb;
   for (int k = 0; k < 48; ++k) rgb.v[k] = h_rgb[k];
-  double* d = nullptr;
-  IIV_CUDA(cudaMalloc(&d, 256 * sizeof(double)));
-  lut_kernel<<<1, 256>>>(rgb, d);
+  static std::mutex mu;     // one result buffer: calls take turns
+  std::lock_guard<std::mutex> lock(mu);
+  lut_kernel<<<1, 256>>>(rgb);
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess)
-    e = cudaMemcpy(h_de, d, 256 * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(d);
+  if (e == cudaSuccess)     // synchronous, and ordered after the kernel on the same stream
+    e = cudaMemcpyFromSymbol(h_de, g_delta_e, 256 * sizeof(double), 0, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return cuda_fail(e, "lut_kernel");
   return 0;
 }
