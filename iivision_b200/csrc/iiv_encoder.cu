@@ -137,8 +137,9 @@ __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
   uint8_t* nb = py_nonce + slot * 624;
   uint8_t* nb2 = py_nonce + (slot == 0 ? kPyBlocks * 624 : slot * 624);
   // three dependent sweeps of 227 / 227 / 170 words; inside a sweep every word is
-  // independent, so the loops are fully unrolled to keep 8 loads in flight per lane
-#pragma unroll
+  // independent.  Unrolled by two only: the opcode loop's roles together are several times
+  // the instruction cache, and this one has time to spare
+#pragma unroll 2
   for (int k = 0; k < 8; ++k) {
     const int t = lane + 32 * k;
     if (t < 227) {
@@ -148,7 +149,7 @@ __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
     }
   }
   __syncwarp();
-#pragma unroll
+#pragma unroll 2
   for (int k = 0; k < 8; ++k) {
     const int t = lane + 32 * k;
     if (t < 227) {
@@ -158,7 +159,7 @@ __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
     }
   }
   __syncwarp();
-#pragma unroll
+#pragma unroll 2
   for (int k = 0; k < 6; ++k) {
     const int t = lane + 32 * k;
     if (t < 169) {
@@ -232,8 +233,11 @@ __device__ __forceinline__ uint4 score_row_regs(const uint64_t* __restrict__ tp_
   return packed_out;
 }
 
+// Out of line on purpose: its one caller is the decision warp's rare "heap ran dry" path,
+// and that warp's loop should stay small (the roles of phase B outgrow the instruction
+// cache several times over).
 template <int MODE>
-__device__ __forceinline__ void score_row(const uint64_t* __restrict__ tp_row,
+__device__ __noinline__ void score_row(const uint64_t* __restrict__ tp_row,
                                           const uint16_t* __restrict__ table,
                                           uint32_t content, int is_aux, int lane,
                                           uint16_t* __restrict__ out_row) {
@@ -788,7 +792,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         int cell, slot, rank, n_cand, n_cont = -1;   // n_cont < 0: evaluate all 256 offsets
         uint32_t content, m8, e8, khi[8], cont = 0;
         uint32_t settled = 0, settled_p = 0;         // words z, w of a front-end record
-        bool have = false;
+        bool have = false, redigest = false;
         if (!heap_done) {
           // ---- next record of the front ends -------------------------------------------
           const int rs = r % kRecRing;
@@ -831,7 +835,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
                 cont = reinterpret_cast<volatile uint32_t*>(sm.rec_cont[rs] + (rec.y >> 30))[lane];
               have = true;
             } else if (reinterpret_cast<volatile int32_t*>(sm.prio)[cell] != 0) {
-              digest(cell, sm.ring_row[slot], khi, m8, e8, rank, n_cand);
+              redigest = true;     // below, at the one call site this warp has
               have = true;
             }
             // else: the cell was zeroed meanwhile -- it would be popped and skipped
@@ -872,8 +876,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           score_row<MODE>(tp + (cell >> 8) * 128, table, content, is_aux, lane,
                           sm.ring_row[kRing]);
           __syncwarp();
-          digest(cell, sm.ring_row[kRing], khi, m8, e8, rank, n_cand);
+          redigest = true;
         }
+        if (redigest) digest(cell, sm.ring_row[slot], khi, m8, e8, rank, n_cand);
         const int page = cell >> 8, off = cell & 255;
         if (MODE == IIV_MODE_DHGR && content >= 0x80u) error_flags |= 1;  // :137
 
