@@ -220,7 +220,8 @@ int iiv_clip_state_layout(size_t* offsets8);
  *                    sum of update_priority before the segment (video.py:90),
  *                    numpy-stream words drawn, python-stream words drawn, then
  *                    tracing counters in SM cycles: score+heapify, opcode loop,
- *                    loop cycles stalled on prefetched rows, on MT19937/applier
+ *                    loop cycles the deciding warp waited for digested heap entries,
+ *                    and for MT19937 blocks / room in the store queue
  */
 int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
                      size_t state_stride, const uint8_t* d_target_mem,
