@@ -24,7 +24,7 @@ lag behind; call ``Video.sync()`` to force a commit mid-generator.
 The speculated budget is a guess at how many opcodes the caller will pull before it
 abandons the generator; ``Movie.encode`` does so at every bank flip (a fixed number of
 opcodes apart) and at every new frame, so the guess is learnt from the generators seen
-so far (``Video._predict``).  A wrong guess costs one more launch, never a different
+so far (``PullPredictor``).  A wrong guess costs one more launch, never a different
 result.  Per generator the host side moves one state blob up and one down through
 page-locked staging buffers; the launch itself allocates nothing.
 
@@ -43,6 +43,47 @@ from .palette import Palette
 from .video_mode import VideoMode
 
 MAX_BUDGET = 2048   # kMaxBudget of csrc/iiv_encoder.cu
+
+
+class PullPredictor:
+    """Guesses how many opcodes the next ``encode_frame`` generator will be asked for.
+
+    ``Movie.encode`` (movie.py:94-102) drops a generator at every bank flip, a fixed number
+    of opcodes after the previous one, and at every new frame.  Both periods are taken from
+    what the caller did so far; until they are known the guess is ``default``.  A wrong
+    guess costs one more kernel launch, never a different result."""
+
+    def __init__(self, default: int, flips: bool, limit: int):
+        self.default, self.flips, self.limit = int(default), bool(flips), int(limit)
+        self._target = None
+        self._aux = None
+        self._since_flip = 0       # opcodes pulled since the bank last changed
+        self._since_frame = 0      # ... since the target last changed
+        self._flip_period = None   # opcodes between the last two bank changes
+        self._frame_period = None  # opcodes pulled for the last complete target
+
+    def guess(self, target, is_aux: bool) -> int:
+        """To be called once per generator, before its first pull."""
+        if target is not self._target and self._target is not None:
+            self._frame_period = self._since_frame
+            self._since_frame = 0
+        if self._aux is not None and bool(is_aux) != self._aux:
+            self._flip_period = self._since_flip
+            self._since_flip = 0
+        self._target, self._aux = target, bool(is_aux)
+        n = self.default
+        if self.flips:
+            period = self._flip_period or self.default
+            if period > self._since_flip:
+                n = period - self._since_flip
+        if self._frame_period and self._frame_period > self._since_frame:
+            n = min(n, self._frame_period - self._since_frame)
+        return max(1, min(n, self.limit))
+
+    def pulled(self, n: int) -> None:
+        """The generator last guessed for was pulled ``n`` times in all."""
+        self._since_flip += n
+        self._since_frame += n
 
 
 class Video:
@@ -94,13 +135,7 @@ class Video:
         self._d_ops = torch.empty((1, MAX_BUDGET, 8), dtype=torch.uint8, device="cuda")
         self._d_info = torch.zeros((1, 1, 8), dtype=torch.int64, device="cuda")
         self._plans = {}
-        # pull statistics behind _predict
-        self._last_target = None
-        self._last_aux = None
-        self._since_flip = 0       # opcodes pulled since the bank last changed
-        self._since_frame = 0      # ... since the target last changed
-        self._flip_period = None   # opcodes between the last two bank changes
-        self._frame_period = None  # opcodes pulled for the last complete target
+        self._predictor = PullPredictor(self.speculate, mode == VideoMode.DHGR, MAX_BUDGET)
 
     def tick(self, ticks: int) -> bool:
         """Keep track of when it is time for a new image frame."""
@@ -157,35 +192,10 @@ class Video:
             plan = self._plans[key] = ops.SegmentPlan([(0, int(is_aux), int(budget))])
         return plan
 
-    # -- how many opcodes will this generator be asked for? ----------------------------------
     def _predict(self, target, is_aux: bool) -> int:
-        """Movie.encode (movie.py:94-102) drops a generator at every bank flip, a fixed
-        number of opcodes after the previous one, and at every new frame.  Both periods are
-        taken from what the caller did so far; until they are known the guess is
-        ``speculate``."""
         if not self._adaptive:
             return self.speculate
-        new_frame = target is not self._last_target
-        flipped = self._last_aux is not None and bool(is_aux) != self._last_aux
-        if new_frame and self._last_target is not None:
-            self._frame_period = self._since_frame
-            self._since_frame = 0
-        if flipped:
-            self._flip_period = self._since_flip
-            self._since_flip = 0
-        self._last_target, self._last_aux = target, bool(is_aux)
-        guess = self.speculate
-        if self.mode == VideoMode.DHGR:
-            period = self._flip_period or self.speculate
-            if period > self._since_flip:
-                guess = period - self._since_flip
-        if self._frame_period and self._frame_period > self._since_frame:
-            guess = min(guess, self._frame_period - self._since_frame)
-        return max(1, min(guess, MAX_BUDGET))
-
-    def _pulled(self, n: int) -> None:
-        self._since_flip += n
-        self._since_frame += n
+        return self._predictor.guess(target, is_aux)
 
     # -- encode_frame ------------------------------------------------------------------------
     def encode_frame(self, target: screen.Bitmap, is_aux: bool
@@ -288,6 +298,6 @@ class _Run:
             self.v._download(self.state_after)
         if not keep:
             self.closed = True
-            self.v._pulled(k)
+            self.v._predictor.pulled(k)
             if self.v._live is self:
                 self.v._live = None

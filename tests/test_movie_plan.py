@@ -72,3 +72,31 @@ def test_plan_degenerate_inputs(movie):
 def test_movie_needs_media_sources(movie):
     with pytest.raises(NotImplementedError):
         movie.Movie("clip.mp4")
+
+
+def test_pull_predictor_learns_the_movie_schedule(movie):
+    """video.PullPredictor fed the generators of plan_movie: once one bank-flip interval and
+    one frame have been seen, every guess is exactly the number of pulls that follows."""
+    from iivision_b200 import video
+    plan = movie.plan_movie("DHGR", 490 * 12, 12, 14700., 30., 2)
+    pred = video.PullPredictor(292, True, video.MAX_BUDGET)
+    targets = {slot: object() for slot in range(len(plan.frames_used))}
+    misses = []
+    for k, (slot, is_aux, count) in enumerate(plan.segments):
+        g = pred.guess(targets[slot], bool(is_aux))
+        assert 1 <= g <= video.MAX_BUDGET
+        if g != count:
+            misses.append(k)
+        pred.pulled(count)
+    first_of_third_frame = next(k for k, s_ in enumerate(plan.segments) if s_[0] == 2)
+    # the first 2 KiB stream frame is one opcode short (header) and so is the first video
+    # frame (tick numbering starts at 1): all learnt by the time the third frame starts
+    assert misses and max(misses) < first_of_third_frame, misses
+    # HGR: no flips, one generator per frame
+    plan = movie.plan_movie("HGR", 490 * 8, 8, 14700., 30., 2)
+    pred = video.PullPredictor(980, False, video.MAX_BUDGET)
+    guesses = []
+    for slot, is_aux, count in plan.segments:
+        guesses.append((pred.guess(object(), False), count))
+        pred.pulled(count)
+    assert all(g == c for g, c in guesses[2:-1]), guesses
