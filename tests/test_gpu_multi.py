@@ -4,7 +4,6 @@ and over NVLink peer stores / NVSwitch multicast, against the single-GPU table."
 import os
 import sys
 
-import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
