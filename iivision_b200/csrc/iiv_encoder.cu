@@ -40,7 +40,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kProducers = 3;            // row-scoring warps (each keeps two rows in flight)
 constexpr int kFronts = 2;               // front-end warps of the opcode loop
-constexpr int kRecRing = 8;              // popped entries digested ahead of the decision warp
+constexpr int kRecRing = 4;              // popped entries digested ahead of the decision warp
 constexpr int kOpQueue = 64;            // emitted opcodes waiting for their stores
 constexpr int kRing = 16;               // prefetched delta rows in flight
 constexpr int kPyBlocks = 4;            // resident 624-word blocks of stream P (power of 2)
@@ -1080,64 +1080,80 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         // Whatever the nonces, the two winners have one of the two smallest deltas among
         // the competing candidates: pass only those on (with their nonce ranks).
         const uint32_t use8 = m8 & e8;
-        uint32_t lane_min = 0xffffffffu;
+        // The lane's two smallest (delta, offset) keys among its competing candidates, then
+        // the warp's two smallest, g1 < g2.
+        uint32_t mine_key = 0xffffffffu, mine_key2 = 0xffffffffu;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if ((use8 >> j) & 1u) lane_min = min(lane_min, khi[j]);
-        const uint32_t d1 = __reduce_min_sync(kFull, lane_min);
-        uint32_t lane_min2 = 0xffffffffu;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (((use8 >> j) & 1u) && khi[j] > d1) lane_min2 = min(lane_min2, khi[j]);
-        const uint32_t d2 = __reduce_min_sync(kFull, lane_min2);
-        uint32_t c8 = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (((use8 >> j) & 1u) && khi[j] <= d2) c8 |= 1u << j;
-        const int mine = __popc(c8);
-        const int n_cont = (int)__reduce_add_sync(kFull, (uint32_t)mine);
-        // With at most one candidate at each of the two smallest deltas the nonces cannot
-        // change the outcome (video.py:295-301 sorts by delta first): settle the winners and
-        // their new diffs here, off the decision warp's chain.  Otherwise hand over the
-        // contenders with their nonce ranks.
-        uint32_t settled = 0, settled_p = 0;
-        if (n_cont <= 1 || (n_cont == 2 && d2 != 0xffffffffu)) {
-          uint32_t mine_key = 0xffffffffu;     // a lane holds both winners only if c8 has 2 bits
-          uint32_t mine_key2 = 0xffffffffu;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if ((c8 >> j) & 1u) {
-              const uint32_t k = (khi[j] << 16) | (uint32_t)(8 * lane + j);
-              mine_key2 = min(mine_key2, max(mine_key, k));
-              mine_key = min(mine_key, k);
-            }
+        for (int j = 0; j < 8; ++j) {
+          if ((use8 >> j) & 1u) {
+            const uint32_t k = (khi[j] << 16) | (uint32_t)(8 * lane + j);
+            mine_key2 = min(mine_key2, max(mine_key, k));
+            mine_key = min(mine_key, k);
           }
-          const uint32_t k1 = __reduce_min_sync(kFull, mine_key);
-          const uint32_t k2 = __reduce_min_sync(kFull, mine_key == k1 ? mine_key2 : mine_key);
+        }
+        const uint32_t g1 = __reduce_min_sync(kFull, mine_key);
+        const uint32_t g2 = __reduce_min_sync(kFull, mine_key == g1 ? mine_key2 : mine_key);
+        // With at most one candidate at each of the two smallest deltas the nonces cannot
+        // change the outcome (video.py:295-301 sorts by delta first): the winners are g1 and
+        // g2, and their new diffs are looked up here, off the decision warp's chain.  That is
+        // the case when g2 does not share g1's delta and nobody else shares g2's.
+        // Otherwise the contenders are handed over with their nonce ranks.
+        uint32_t settled = 0, settled_p = 0;
+        int n_cont = 0;
+        bool unique = g2 == 0xffffffffu;
+        if (!unique && (g1 >> 16) != (g2 >> 16)) {
+          bool rival = false;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            rival |= ((use8 >> j) & 1u) && khi[j] == (g2 >> 16) &&
+                     (uint32_t)(8 * lane + j) != (g2 & 0xffffu);
+          unique = __ballot_sync(kFull, rival) == 0;
+        }
+        if (unique) {
           settled = 1u << 26;
-          if (k1 != 0xffffffffu) {
-            const uint32_t w1 = k1 & 255u;
+          if (g1 != 0xffffffffu) {
+            const uint32_t w1 = g1 & 255u;
             settled |= w1 | (1u << 27);
             settled_p = reinterpret_cast<const volatile uint16_t*>(row)[w1];
+            n_cont = 1;
           }
-          if (k2 != 0xffffffffu) {
-            const uint32_t w2 = k2 & 255u;
+          if (g2 != 0xffffffffu) {
+            const uint32_t w2 = g2 & 255u;
             settled |= (w2 << 8) | (1u << 28);
             settled_p |= (uint32_t)reinterpret_cast<const volatile uint16_t*>(row)[w2] << 16;
+            n_cont = 2;
           }
-        } else if (n_cont <= 32) {
+        } else {
+          // whatever the nonces, the two winners have one of the two smallest deltas
+          const uint32_t d1 = g1 >> 16;
+          uint32_t d2 = g2 >> 16;
+          if (d2 == d1) {
+            uint32_t lane_min2 = 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (((use8 >> j) & 1u) && khi[j] > d1) lane_min2 = min(lane_min2, khi[j]);
+            d2 = __reduce_min_sync(kFull, lane_min2);
+          }
+          uint32_t c8 = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (((use8 >> j) & 1u) && khi[j] <= d2) c8 |= 1u << j;
+          const int mine = __popc(c8);
           int incl = mine;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
             const int v = __shfl_up_sync(kFull, incl, d);
             if (lane >= d) incl += v;
           }
-          int at = incl - mine;
+          n_cont = __shfl_sync(kFull, incl, 31);
+          if (n_cont <= 32) {
+            int at = incl - mine;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if ((c8 >> j) & 1u) {
-              const uint32_t nrank = (uint32_t)(rank + __popc(m8 & ((1u << j) - 1u)));
-              sm.rec_cont[rs][at++] = (khi[j] << 16) | (nrank << 8) | (uint32_t)(8 * lane + j);
+            for (int j = 0; j < 8; ++j) {
+              if ((c8 >> j) & 1u) {
+                const uint32_t nrank = (uint32_t)(rank + __popc(m8 & ((1u << j) - 1u)));
+                sm.rec_cont[rs][at++] = (khi[j] << 16) | (nrank << 8) | (uint32_t)(8 * lane + j);
+              }
             }
           }
         }
