@@ -100,3 +100,42 @@ def test_pull_predictor_learns_the_movie_schedule(movie):
         guesses.append((pred.guess(object(), False), count))
         pred.pulled(count)
     assert all(g == c for g, c in guesses[2:-1]), guesses
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_plan_plus_oracle_encoder_reproduces_reference_bytes(movie, oracle_tables, case):
+    """The whole movie on the CPU: plan_movie's generators run through the numpy oracle of
+    the encoder, the tuples through the host muxer -- against the bytes the unmodified
+    reference's Movie.encode + emit_stream produced.  Pins the schedule (which opcode comes
+    from which frame/bank generator) and the oracle's encoder on a full-length run."""
+    import random
+    from iivision_b200 import opcodes, video_mode
+    from oracle import scorer
+    b = np.load(os.path.join(GOLDEN, "byte_stream.npz"))
+    opcodes.set_addresses(b["tick_addr"], int(b["ack_addr"]), int(b["terminate_addr"]))
+    g = np.load(os.path.join(GOLDEN, "movie_%s.npz" % case))
+    mode = str(g["mode"])
+    frames, samples = g["frames"], g["audio"]
+    plan = _plan(movie, g)
+    seed = int(g["rng_seed"])
+    v = scorer.OracleVideo(mode, oracle_tables(mode), py_rng=random.Random(seed),
+                           np_rng=np.random.RandomState(seed))
+    vm = getattr(video_mode.VideoMode, mode)
+    ops_ = [opcodes.Header(mode=vm)]
+    tick = 0
+    for slot, is_aux, count in plan.segments:
+        fr = plan.frames_used[slot]
+        tgt = v.target_bitmap(frames[fr, 0], frames[fr, 1] if mode == "DHGR" else None)
+        seq = v.encode_frame(tgt, bool(is_aux))
+        for _ in range(count):
+            page, content, offs = next(seq)
+            if tick < plan.emitted:
+                ops_.append(opcodes.TICK_OPCODES[(2 * int(samples[tick]) + 34, int(page))](
+                    int(content), tuple(int(o) for o in offs)))
+            tick += 1
+    assert tick == plan.pulled
+    mux = movie.StreamMuxer(vm, max_bytes_out=int(g["max_bytes_out"]) or None)
+    data = bytes(mux.emit_stream(ops_))
+    assert data == g["bytes"].tobytes()
+    assert np.array_equal(v.pixelmap.packed, g["packed"])
+    assert np.array_equal(v.update_priority, g["priority_main"])
