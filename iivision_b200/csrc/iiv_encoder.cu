@@ -40,7 +40,10 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kProducers = 3;            // row-scoring warps (each keeps two rows in flight)
 constexpr int kFronts = 2;               // front-end warps of the opcode loop
-constexpr int kRecRing = 4;              // popped entries digested ahead of the decision warp
+// popped entries digested ahead of the decision warp: enough for the front ends to stay busy,
+// no more -- the further ahead they read a page, the more often it has changed by the time
+// the record is used (8 measured 1-2 % slower, 2 starves the decision warp)
+constexpr int kRecRing = 4;
 constexpr int kOpQueue = 64;            // emitted opcodes waiting for their stores
 constexpr int kRing = 16;               // prefetched delta rows in flight
 constexpr int kPyBlocks = 4;            // resident 624-word blocks of stream P (power of 2)
