@@ -139,3 +139,41 @@ def test_plan_plus_oracle_encoder_reproduces_reference_bytes(movie, oracle_table
     assert data == g["bytes"].tobytes()
     assert np.array_equal(v.pixelmap.packed, g["packed"])
     assert np.array_equal(v.update_priority, g["priority_main"])
+
+
+def test_plan_properties_random(movie):
+    """plan_movie against the C library's stream arithmetic and its own invariants on random
+    parameters (hypothesis is not needed for this: a seeded sweep)."""
+    from iivision_b200._lib import lib
+    rng = np.random.default_rng(17)
+    for _ in range(300):
+        mode = "DHGR" if rng.random() < 0.6 else "HGR"
+        n_samples = int(rng.integers(0, 6000))
+        n_frames = int(rng.integers(0, 12))
+        fps = float(rng.choice([23.976, 24., 25., 29.97, 30., 60.]))
+        every = int(rng.integers(1, 4))
+        cap = int(rng.integers(1, 40000)) if rng.random() < 0.5 else None
+        free = movie.plan_movie(mode, n_samples, n_frames, 14700., fps, every, None)
+        plan = movie.plan_movie(mode, n_samples, n_frames, 14700., fps, every, cap)
+        assert free.emitted == free.pulled <= n_samples
+        assert sum(s[2] for s in plan.segments) == plan.pulled
+        assert all(s[2] > 0 for s in plan.segments)
+        if cap is None:
+            assert plan == free
+            continue
+        within = int(lib.iiv_stream_ticks_within(free.emitted, cap))
+        assert plan.emitted == within
+        # the opcode that finds the stream full is computed, then dropped
+        assert plan.pulled == within + (1 if within < free.pulled else 0)
+        # a capped plan is a prefix of the free one
+        flat_free = [(s[0], s[1]) for s in free.segments for _ in range(s[2])]
+        flat_cap = [(s[0], s[1]) for s in plan.segments for _ in range(s[2])]
+        assert flat_cap == flat_free[:len(flat_cap)]
+        if mode == "HGR":
+            assert all(s[1] == 0 for s in plan.segments)
+        else:
+            # the bank of tick k is decided by how many Acks precede it: 291, then every 292
+            for k, (_, is_aux) in enumerate(flat_free[:2000:37]):
+                kk = k * 37
+                flips = 0 if kk < 291 else 1 + (kk - 291) // 292
+                assert is_aux == flips % 2
