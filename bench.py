@@ -231,89 +231,208 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def scorer_figures(torch, ops, single=True):
-    """Second hot path, DHGR NTSC: (a) scoring primitives batched over frames
-    (pack + diff_weights + every delta row), (b) bit-exact encoding of
-    independent clips, one block per clip."""
+def golden_streams():
+    """Reference digests of the named scorer workloads (tests/golden/long_streams.json,
+    written by oracle/make_golden.py --long-only from the unmodified reference)."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "long_streams.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
+def _encode_setup(torch, ops, clips, seeds_unused=None):
+    """clips uint8[n_clips, n_frames, 2, 32, 256] -> (target memory, packed targets)."""
+    import numpy as np
+    tmem = torch.from_numpy(np.ascontiguousarray(clips)).cuda()
+    n_clips, n_frames = tmem.shape[0], tmem.shape[1]
+    flat = tmem.view(-1, 2, 32, 256)
+    tpacked = ops.pack("DHGR", flat[:, 0].contiguous(), flat[:, 1].contiguous()).view(
+        n_clips, n_frames, 32, 128)
+    return tmem, tpacked
+
+
+def _timed_encode(torch, ops, tmem, tpacked, plan, table, seeds, reps, warm=2):
+    """Median CUDA-event time of `reps` encode launches from fresh states; returns
+    (ms, all ms sorted, opcodes of the last run, seg_info, states)."""
+    n_clips = tmem.shape[0]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    # outputs are allocated once: a fresh cudaMalloc between the two events would be
+    # charged to the kernel
+    opc = torch.empty((n_clips, plan.total, 8), dtype=torch.uint8, device="cuda")
+    info = torch.zeros((n_clips, len(plan), 8), dtype=torch.int64, device="cuda")
+    times = []
+    st = None
+    for r in range(reps + warm):
+        st = ops.seed_clip_states(ops.new_clip_states(n_clips), seeds)
+        torch.cuda.synchronize()
+        ev[0].record()
+        ops.encode_clips("DHGR", st, tmem, tpacked, plan, table, opcodes=opc, seg_info=info)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if r >= warm:
+            times.append(ev[0].elapsed_time(ev[1]))
+    times.sort()
+    return times[len(times) // 2], times, opc, info, st
+
+
+def _trace(info):
+    inf = info.cpu().numpy()
+    cyc = inf[0].sum(axis=0)
+    return {"slowest_clip_sm_cycles": int((inf[:, :, 4] + inf[:, :, 5]).sum(axis=1).max()),
+            "opcodes": int(cyc[0]), "cycles_score_heapify": int(cyc[4]),
+            "cycles_opcode_loop": int(cyc[5]), "cycles_wait_rows": int(cyc[6]),
+            "cycles_wait_mt_applier": int(cyc[7])}
+
+
+def phase_a_figures(torch, ops, table):
+    """Scoring prologue of Video._index_changes (video.py:109-116) batched over DISTINCT
+    frames: one iiv_score_frames launch packs every target, scores both banks against the
+    previous frame's bitmap and folds the priorities."""
+    from iivision_b200 import synth
+    nb = int(os.environ.get("IIV_BENCH_SCORE_FRAMES", "1024"))
+    fr = synth.synthetic_frames("DHGR", nb + 1, 1.0, seed=1)
+    d = torch.from_numpy(fr).cuda()
+    src = ops.pack("DHGR", d[:nb, 0].contiguous(), d[:nb, 1].contiguous())
+    tgt = d[1:].contiguous()
+    prio = torch.zeros((nb, 2, 32, 256), dtype=torch.int32, device="cuda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for _ in range(3):
+        ops.score_frames("DHGR", src, tgt, table, priority=prio)
+    torch.cuda.synchronize()
+    reps = 20
+    ev[0].record()
+    for _ in range(reps):
+        ops.score_frames("DHGR", src, tgt, table, priority=prio)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / reps
+    peaks, peak_src = measured_peaks()
+    # SURVEY 8(d): one diff_weights bank call = 2 x 32 KiB packed in + 32 KiB int32 out +
+    # 8192 x 2 B of table = 112 KiB algorithmic, 8192 x 32 B = 256 KiB of sectors; a DHGR
+    # frame is two bank calls.  What the fused launch really streams per frame on top of the
+    # gathers: 16 KiB screen bytes + 32 KiB source in, 32 KiB packed target + 64 KiB diff
+    # out, 64 KiB priorities in and out.
+    alg = 2 * 112 * 1024 * nb
+    sector = 2 * 8192 * 32 * nb
+    streamed = (16 + 32 + 32 + 64 + 128) * 1024 * nb
+    achieved = alg / (ms * 1e-3) / 1e9
+    return {
+        "scored_frames_per_s": nb / (ms * 1e-3),
+        "scored_frames_note": (
+            "iiv_score_frames: pack + diff_weights (main+aux) + hole mask + priority fold of "
+            "%d DISTINCT DHGR frames per launch (source = the previous frame), device "
+            "resident; %.1f MB streamed per launch (> L2) + %d random table gathers" % (
+                nb, streamed / 1e6, 2 * 8192 * nb)),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                     "peak_source": peak_src, "kernel": "score_frames_kernel",
+                     "kernel_ms": ms, "algorithmic_bytes_per_launch": alg,
+                     "gather_sector_bytes_per_launch": sector,
+                     "streamed_bytes_per_launch": streamed,
+                     "sector_plus_streamed_gbs": (sector + streamed) / (ms * 1e-3) / 1e9,
+                     "note": "algorithmic = 112 KiB per bank call (SURVEY 8(d)) x 2 banks x "
+                             "frames; the gathers are uniform over the 512 MiB table (random "
+                             "frames), each costing a 32 B sector"},
+    }
+
+
+def long_clip_figures(torch, ops, table):
+    """BASELINE.json configs[3]: the 6000-frame DHGR clip, one launch, its first 600 frames
+    checked against the digests of the unmodified reference."""
+    from iivision_b200 import synth
+    lc = synth.LONG_CLIP
+    n = int(os.environ.get("IIV_BENCH_LONG_FRAMES", str(lc["n_frames"])))
+    frames = synth.long_clip_frames(n)
+    plan = ops.SegmentPlan(synth.movie_schedule("DHGR", n))
+    tmem, tpacked = _encode_setup(torch, ops, frames[None])
+    ms, all_ms, opc, info, _ = _timed_encode(torch, ops, tmem, tpacked, plan, table,
+                                             [lc["rng_seed"]], reps=1, warm=0)
+    out = {"frames": n, "opcodes": plan.total, "ms": ms,
+           "frames_per_s": n / (ms * 1e-3), "us_per_opcode": ms * 1e3 / plan.total,
+           "real_opcodes": int(info.cpu().numpy()[0][:, 0].sum()),
+           "note": "one DHGR clip, one thread block, one launch; 980 opcodes per frame, "
+                   "bank flip every 292 (Movie.encode schedule)"}
+    gold = golden_streams()
+    if gold is not None:
+        got = opc.cpu().numpy()[0]
+        checks = {}
+        for frames_done, want in gold["long"]["opcode_sha256"].items():
+            k = int(frames_done)
+            if k <= n:
+                checks[frames_done] = synth.opcode_digest(got[:k * 980]) == want
+        out["reference_digest_frames"] = max([int(k) for k in checks] or [0])
+        out["matches_reference"] = bool(checks) and all(checks.values())
+    return out
+
+
+def batch_clips_figures(torch, ops, table, world=1, rank=0, dist=None):
+    """BASELINE.json configs[4]: 64 independent DHGR clips, clip-per-GPU sharding (8 per
+    GPU at N = 8), no collective on the data path; the clips whose reference digests are
+    committed are checked on whichever rank holds them."""
+    import numpy as np
+    from iivision_b200 import parallel, synth
+    bc = synth.BATCH_CLIPS
+    lo, hi = parallel.shard_range(bc["n_clips"], world, rank)
+    n = bc["n_frames"]
+    clips = np.stack([synth.batch_clip_frames(c) for c in range(lo, hi)])
+    seeds = [synth.batch_clip_seeds(c)[1] for c in range(lo, hi)]
+    plan = ops.SegmentPlan(synth.movie_schedule("DHGR", n))
+    tmem, tpacked = _encode_setup(torch, ops, clips)
+    if dist is not None and world > 1:
+        dist.barrier()
+    ms, all_ms, opc, info, _ = _timed_encode(torch, ops, tmem, tpacked, plan, table, seeds,
+                                             reps=5)
+    ok, checked = 1, 0
+    gold = golden_streams()
+    if gold is not None:
+        got = opc.cpu().numpy()
+        for key, g in gold["batch"].items():
+            c = int(key)
+            if lo <= c < hi:
+                checked += 1
+                if synth.opcode_digest(got[c - lo]) != g["opcode_sha256"][str(n)]:
+                    ok = 0
+    if dist is not None and world > 1:
+        t = torch.tensor([ms, -float(ok), float(checked)], device="cuda", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ok, checked = float(tmax[0]), int(-tmax[1].item()), int(tsum[2].item())
+    return {"clips": bc["n_clips"], "frames_per_clip": n, "clips_per_gpu": hi - lo,
+            "n_gpus": world, "ms": ms,
+            "encoded_frames_per_s": bc["n_clips"] * n / (ms * 1e-3),
+            "reference_digest_clips": checked,
+            "matches_reference": bool(ok) if gold is not None else None,
+            "note": "64 distinct DHGR clips x 32 frames (distinct frame and RNG seeds), "
+                    "clips sharded contiguously over the GPUs, one thread block per clip; "
+                    "slowest rank's median CUDA-event time of 5 launches"}
+
+
+def scorer_figures(torch, ops, single=True, world=1, rank=0, dist=None):
+    """Second hot path, DHGR NTSC, on DISTINCT synthetic data everywhere: (a) the scoring
+    prologue batched over frames, (b) bit-exact encoding of independent clips, one block
+    per clip, (c) the named configs[3] / configs[4] workloads with their reference
+    digests checked inside the run."""
     import numpy as np
     from iivision_b200 import palette, synth
     lut = ops.lut_cie2000(palette.NTSCPalette.rgb_by_value())
     table = ops.table_generate("DHGR", lut, layout=ops.LAYOUT_SYMMETRIC)
     out = {}
-    # (a) phase A over a batch of 256 frame pairs
-    nb = 256
-    fr = synth.synthetic_frames("DHGR", 2, 1.0, seed=1)
-    main = torch.from_numpy(fr[:, 0]).cuda().repeat(nb // 2, 1, 1).contiguous()
-    aux = torch.from_numpy(fr[:, 1]).cuda().repeat(nb // 2, 1, 1).contiguous()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-
-    def phase_a():
-        packed = ops.pack("DHGR", main, aux)
-        src = torch.roll(packed, 1, 0).contiguous()
-        for is_aux in (0, 1):
-            ops.diff_weights("DHGR", is_aux, src, packed, table)
-    for _ in range(3):
-        phase_a()
-    torch.cuda.synchronize()
-    ev[0].record()
-    reps = 10
-    for _ in range(reps):
-        phase_a()
-    ev[1].record()
-    torch.cuda.synchronize()
-    out["scored_frames_per_s"] = nb * reps / (ev[0].elapsed_time(ev[1]) * 1e-3)
-    out["scored_frames_note"] = ("pack + diff_weights (main+aux banks) of %d DHGR frames "
-                                 "per launch set, device resident" % nb)
-    # (b) encoder: independent clips under the Movie.encode schedule (980 opcodes per
-    # frame, bank flip every 292), one thread block per clip, bit-exact streams
-    import random
-    mt_py = ops.mt_from_python(random.Random(0).getstate())
-    mt_np = ops.mt_from_numpy(np.random.RandomState(0).get_state())
+    out["config4_batch_clips"] = batch_clips_figures(torch, ops, table, world, rank, dist)
+    if not single:
+        return out
+    out.update(phase_a_figures(torch, ops, table))
 
     def encode_run(n_clips, n_frames, reps=5):
         clips = np.stack([synth.synthetic_frames("DHGR", n_frames, 1.0, seed=100 + c)
-                          for c in range(min(n_clips, 4))])
-        clips = np.concatenate([clips] * (n_clips // clips.shape[0] + 1))[:n_clips]
-        segs = synth.movie_schedule("DHGR", n_frames)
-        plan = ops.SegmentPlan(segs)      # schedule resident on the device: pure launches
-        tmem = torch.from_numpy(np.ascontiguousarray(clips)).cuda()
-        flat = tmem.view(-1, 2, 32, 256)
-        tpacked = ops.pack("DHGR", flat[:, 0].contiguous(), flat[:, 1].contiguous()).view(
-            n_clips, n_frames, 32, 128)
-
-        def fresh_states():
-            st = ops.new_clip_states(n_clips)
-            pad = np.zeros(640, np.uint32)
-            pad[:625] = mt_py
-            ops.state_field(st, ops.F_MT_PY, torch.int32, (640,)).copy_(
-                torch.from_numpy(pad.view(np.int32)).cuda().expand(n_clips, 640))
-            pad[:625] = mt_np
-            ops.state_field(st, ops.F_MT_NP, torch.int32, (640,)).copy_(
-                torch.from_numpy(pad.view(np.int32)).cuda().expand(n_clips, 640))
-            return st
-        times = []
-        total_budget = int(sum(s_[2] for s_ in segs))
-        # outputs are allocated once: a fresh cudaMalloc between the two events would be
-        # charged to the kernel
-        opc = torch.empty((n_clips, total_budget, 8), dtype=torch.uint8, device="cuda")
-        info = torch.zeros((n_clips, len(segs), 8), dtype=torch.int64, device="cuda")
-        for r in range(reps + 2):
-            st = fresh_states()
-            torch.cuda.synchronize()
-            ev[0].record()
-            ops.encode_clips("DHGR", st, tmem, tpacked, plan, table, opcodes=opc, seg_info=info)
-            ev[1].record()
-            torch.cuda.synchronize()
-            if r >= 2:
-                times.append(ev[0].elapsed_time(ev[1]))
-        times.sort()
-        inf = info.cpu().numpy()
-        cyc = inf[0].sum(axis=0)
-        trace = {"slowest_clip_sm_cycles": int((inf[:, :, 4] + inf[:, :, 5]).sum(axis=1).max()),
-                 "opcodes": int(cyc[0]), "cycles_score_heapify": int(cyc[4]),
-                 "cycles_opcode_loop": int(cyc[5]), "cycles_wait_rows": int(cyc[6]),
-                 "cycles_wait_mt_applier": int(cyc[7])}
-        return times[len(times) // 2], times, trace
+                          for c in range(n_clips)])
+        plan = ops.SegmentPlan(synth.movie_schedule("DHGR", n_frames))
+        tmem, tpacked = _encode_setup(torch, ops, clips)
+        ms, times, _, info, _ = _timed_encode(torch, ops, tmem, tpacked, plan, table,
+                                              [7 + c for c in range(n_clips)], reps)
+        return ms, times, _trace(info)
 
     n_clips, n_frames = int(os.environ.get("IIV_BENCH_CLIPS", "148")), 4
     sampler = ClockSampler(torch.cuda.current_device())
@@ -322,15 +441,21 @@ def scorer_figures(torch, ops, single=True):
     ms, all_ms, trace = encode_run(n_clips, n_frames, reps=25)
     out["encoded_trace_clip0"] = trace
     out["encoded_frames_per_s"] = n_clips * n_frames / (ms * 1e-3)
-    out["encoded_note"] = ("%d independent DHGR clips x %d frames, one block per clip; median "
-                           "of %d runs (ms min/median/max: %.2f / %.2f / %.2f)" % (
-                               n_clips, n_frames, len(all_ms), all_ms[0], ms, all_ms[-1]))
+    out["encoded_note"] = ("%d DISTINCT DHGR clips (own frames, own RNG seeds) x %d frames, one "
+                           "block per clip; median of %d runs (ms min/median/max: %.2f / %.2f / "
+                           "%.2f)" % (n_clips, n_frames, len(all_ms), all_ms[0], ms, all_ms[-1]))
     out["encoded_clocks"] = sampler.summary(t_enc0, time.perf_counter())
     sampler.stop()
     sm_mhz = out["encoded_clocks"].get("sm_mhz") or 1965.0
     out["encoded_ms_from_sm_cycles"] = trace["slowest_clip_sm_cycles"] / (sm_mhz * 1e3)
-    if not single:
-        return out
+    ms2, all2, _ = encode_run(2 * n_clips, n_frames, reps=9)
+    out["encoded_frames_per_s_2_waves"] = 2 * n_clips * n_frames / (ms2 * 1e-3)
+    out["encoded_2_waves_note"] = "%d distinct clips (two per SM, run in waves): %.2f ms" % (
+        2 * n_clips, ms2)
+    try:
+        out["config3_long_clip"] = long_clip_figures(torch, ops, table)
+    except Exception as e:   # noqa: BLE001
+        out["config3_long_clip"] = {"error": repr(e)}
     # BASELINE.json configs[0]: HGR NTSC, one 60-frame 280x192 clip (980 opcodes per frame,
     # a single bank), next to the reference's algorithm on the host: oracle/scorer.py keeps
     # the reference's cost structure (whole-array numpy calls per opcode, heapq, Python RNG
@@ -736,20 +861,14 @@ def run_ours(args, rank, world, local_rank):
     if sampler:
         sampler.stop()
 
-    # second hot path at N > 1: independent clips shard clip-per-GPU, no collective on
-    # the data path; every rank encodes its own 148 clips and the job's rate is the sum
+    # second hot path at N > 1: BASELINE.json configs[4], 64 distinct clips sharded
+    # clip-per-GPU with no collective on the data path (every rank takes part)
     clips_multi = None
     if world > 1 and not args.no_scorer:
         try:
-            fig = scorer_figures(torch, ops, single=False)
-            t = torch.tensor([148 * 4 / fig["encoded_frames_per_s"]], device="cuda",
-                             dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            clips_multi = {
-                "encoded_frames_per_s": world * 148 * 4 / float(t.item()),
-                "encoded_note": "%d x 148 independent DHGR clips x 4 frames, clip-per-GPU "
-                                "sharding (weak scaling), slowest rank's time" % world}
-        except Exception as e:
+            clips_multi = scorer_figures(torch, ops, single=False, world=world, rank=rank,
+                                         dist=dist)
+        except Exception as e:   # noqa: BLE001
             clips_multi = {"error": repr(e)}
     if rank != 0:
         return

@@ -48,6 +48,9 @@ PROTOTYPES = {
                                          c_void_p]),
     "iiv_diff_weights": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "iiv_score_frames": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                 c_void_p]),
     "iiv_diff_weights_page": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int,
                                       c_void_p, c_void_p, c_int, c_void_p]),
     "iiv_compute_delta_page": (c_int, [c_int, c_int, c_void_p, c_int, c_int,

@@ -131,6 +131,131 @@ diff_weights_kernel(int is_aux, const uint64_t* __restrict__ src,
   reinterpret_cast<int2*>(out)[c] = res;
 }
 
+// ---- Video._index_changes' scoring prologue for a batch of frames ---------------------
+// video.py:109-116 (diff_weights of the target against the source bitmap, holes zeroed,
+// priorities folded) fused with Bitmap._pack of the target (screen.py:207-226), both banks
+// of a DHGR frame in one pass.  A block owns 8 pages (1024 packed columns) of one frame, a
+// thread 4 adjacent columns: it builds their packed target words from the raw screen bytes
+// (its own 8 bytes of each bank plus the neighbouring column on either side for header and
+// footer), reads 32 bytes of packed source, and issues all of its table gathers -- 4
+// columns x 2 byte offsets x banks = 16 (DHGR) / 8 (HGR) independent loads -- before it
+// touches any result.  Outputs leave as 16-byte stores: 32 B of packed target, 32 B of
+// diff weights and 32 B of priorities per thread and bank.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+score_frames_kernel(const uint64_t* __restrict__ src, size_t src_stride,
+                    const uint8_t* __restrict__ tmain, const uint8_t* __restrict__ taux,
+                    size_t mem_stride, const uint16_t* __restrict__ table,
+                    uint64_t* __restrict__ tpacked, int32_t* __restrict__ diff,
+                    int32_t* __restrict__ prio, int zero_holes) {
+  using M = Mode<MODE>;
+  constexpr int kBanks = MODE == IIV_MODE_DHGR ? 2 : 1;
+  const size_t frame = blockIdx.y;
+  const int c0 = blockIdx.x * 1024 + 4 * threadIdx.x;   // first of 4 columns, one page
+  const int col = c0 & 127;
+  const uint8_t* mm = tmain + frame * mem_stride + 2 * c0;
+  const uint8_t* am = MODE == IIV_MODE_DHGR ? taux + frame * mem_stride + 2 * c0 : nullptr;
+  // bytes of columns c0-1 .. c0+4 (12 bytes per bank); outside the page: zeros, which give
+  // the zero header / footer of screen.py:217, :224
+  uint8_t mb[12], ab[12];
+  {
+    const uint2 w = *reinterpret_cast<const uint2*>(mm);
+    const uchar2 p = col > 0 ? *reinterpret_cast<const uchar2*>(mm - 2) : make_uchar2(0, 0);
+    const uchar2 n = col < 124 ? *reinterpret_cast<const uchar2*>(mm + 8) : make_uchar2(0, 0);
+    mb[0] = p.x; mb[1] = p.y; mb[10] = n.x; mb[11] = n.y;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      mb[2 + k] = (uint8_t)(w.x >> (8 * k));
+      mb[6 + k] = (uint8_t)(w.y >> (8 * k));
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) ab[k] = 0;
+  if (MODE == IIV_MODE_DHGR) {
+    const uint2 w = *reinterpret_cast<const uint2*>(am);
+    const uchar2 p = col > 0 ? *reinterpret_cast<const uchar2*>(am - 2) : make_uchar2(0, 0);
+    const uchar2 n = col < 124 ? *reinterpret_cast<const uchar2*>(am + 8) : make_uchar2(0, 0);
+    ab[0] = p.x; ab[1] = p.y; ab[10] = n.x; ab[11] = n.y;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ab[2 + k] = (uint8_t)(w.x >> (8 * k));
+      ab[6 + k] = (uint8_t)(w.y >> (8 * k));
+    }
+  }
+  uint64_t body[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    body[k] = body_of<MODE>(mb[2 * k], mb[2 * k + 1], ab[2 * k], ab[2 * k + 1]);
+  uint64_t tp[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    // header[:,0] = 0, footer[:,-1] = 0: the zero bodies above stand in at the page edges,
+    // but a zero BODY is not a zero header for HGR only if bits leak -- header_of(0) == 0
+    tp[k] = header_of<MODE>(body[k]) ^ body[k + 1] ^ footer_of<MODE>(body[k + 2]);
+  }
+  const uint64_t* sp = src + frame * src_stride + c0;
+  const ulonglong2 s01 = *reinterpret_cast<const ulonglong2*>(sp);
+  const ulonglong2 s23 = *reinterpret_cast<const ulonglong2*>(sp + 2);
+  const uint64_t sw[4] = {s01.x, s01.y, s23.x, s23.y};
+  if (tpacked != nullptr) {
+    uint64_t* o = tpacked + frame * 4096 + c0;
+    *reinterpret_cast<ulonglong2*>(o) = make_ulonglong2(tp[0], tp[1]);
+    *reinterpret_cast<ulonglong2*>(o + 2) = make_ulonglong2(tp[2], tp[3]);
+  }
+  uint32_t idx[kBanks][8];
+#pragma unroll
+  for (int b = 0; b < kBanks; ++b)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int o = byte_offset<MODE>(half, b);
+        idx[b][2 * k + half] = ((uint32_t)o << (2 * M::kBits)) +
+                               (mask_shift<MODE>(sw[k], o) << M::kBits) +
+                               mask_shift<MODE>(tp[k], o);
+      }
+  int32_t dw[kBanks][8];
+#pragma unroll
+  for (int b = 0; b < kBanks; ++b)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dw[b][k] = (int32_t)__ldg(table + idx[b][k]);
+  // the priorities stream in while the gathers are in flight
+  int4 pin[kBanks][2];
+  if (prio != nullptr) {
+#pragma unroll
+    for (int b = 0; b < kBanks; ++b) {
+      const int4* pp =
+          reinterpret_cast<const int4*>(prio + (frame * kBanks + b) * 8192 + 2 * (size_t)c0);
+      pin[b][0] = pp[0];
+      pin[b][1] = pp[1];
+    }
+  }
+  const bool hole = zero_holes && (col == 60 || col == 124);   // offsets 120..127, 248..255
+#pragma unroll
+  for (int b = 0; b < kBanks; ++b) {
+    if (hole) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dw[b][k] = 0;                // video.py:111
+    }
+    const size_t at = (frame * kBanks + b) * 8192 + 2 * (size_t)c0;
+    if (diff != nullptr) {
+      int4* d = reinterpret_cast<int4*>(diff + at);
+      d[0] = make_int4(dw[b][0], dw[b][1], dw[b][2], dw[b][3]);
+      d[1] = make_int4(dw[b][4], dw[b][5], dw[b][6], dw[b][7]);
+    }
+    if (prio != nullptr) {
+      int4* pp = reinterpret_cast<int4*>(prio + at);
+      const int4 p0 = pin[b][0], p1 = pin[b][1];
+      int32_t pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        pv[k] = (dw[b][k] == 0 ? 0 : pv[k]) + dw[b][k];        // video.py:115-116
+      pp[0] = make_int4(pv[0], pv[1], pv[2], pv[3]);
+      pp[1] = make_int4(pv[4], pv[5], pv[6], pv[7]);
+    }
+  }
+}
+
 // compute_delta_page (screen.py:525-547) for one (page, content).
 template <int MODE>
 __global__ void __launch_bounds__(128)
@@ -326,6 +451,28 @@ extern "C" int iiv_diff_weights(int mode, int is_aux, const uint64_t* d_source_p
   const size_t n_cols = (size_t)batch * 4096;
   IIV_DISPATCH(mode, diff_weights_kernel, (unsigned)((n_cols + 255) / 256), 256, st,
                is_aux, d_source_packed, d_target_packed, content, d_table, d_out, n_cols);
+  return 0;
+}
+
+extern "C" int iiv_score_frames(int mode, const uint64_t* d_source_packed, size_t source_stride,
+                                const uint8_t* d_target_main, const uint8_t* d_target_aux,
+                                size_t mem_stride, const uint16_t* d_table,
+                                uint64_t* d_target_packed, int32_t* d_diff, int32_t* d_priority,
+                                int zero_holes, int batch, void* stream) {
+  IIV_REQUIRE(mode_ok(mode), "bad mode %d", mode);
+  IIV_REQUIRE(d_source_packed && d_target_main && d_table && batch >= 0 && batch <= 65535,
+              "bad argument");
+  IIV_REQUIRE(mode == IIV_MODE_HGR || d_target_aux, "DHGR needs aux memory");
+  IIV_REQUIRE(mem_stride % 8 == 0 && source_stride % 2 == 0, "strides must keep 8/16-byte alignment");
+  IIV_REQUIRE(((uintptr_t)d_target_main % 8) == 0 && ((uintptr_t)d_target_aux % 8) == 0 &&
+                  ((uintptr_t)d_source_packed % 16) == 0 && ((uintptr_t)d_target_packed % 16) == 0 &&
+                  ((uintptr_t)d_diff % 16) == 0 && ((uintptr_t)d_priority % 16) == 0,
+              "misaligned buffer");
+  if (batch == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  IIV_DISPATCH(mode, score_frames_kernel, dim3(4, batch), 256, st, d_source_packed,
+               source_stride, d_target_main, d_target_aux, mem_stride, d_table,
+               d_target_packed, d_diff, d_priority, zero_holes);
   return 0;
 }
 

@@ -270,6 +270,45 @@ def diff_weights(mode, is_aux, source_packed: torch.Tensor,
     return out
 
 
+def score_frames(mode, source_packed: torch.Tensor, target_mem: torch.Tensor,
+                 table: torch.Tensor, priority: torch.Tensor = None,
+                 zero_holes: bool = True, want_packed: bool = True, want_diff: bool = True):
+    """The scoring prologue of Video._index_changes (video.py:109-116) for a batch of
+    frames in one launch: pack every target, diff_weights of every bank against the
+    source bitmap(s), holes zeroed, priorities folded in place.
+
+    source_packed int64[batch, 32, 128] or [32, 128] (one source for all frames);
+    target_mem uint8[batch, banks, 32, 256]; priority int32[batch, banks, 32, 256] or
+    None.  Returns (target_packed int64[batch, 32, 128] | None, diff int32[batch, banks,
+    32, 256] | None)."""
+    m = mode_id(mode)
+    banks = 2 if m == MODE_DHGR else 1
+    batch = target_mem.shape[0]
+    if target_mem.dtype != torch.uint8 or tuple(target_mem.shape[1:]) != (banks, 32, 256):
+        raise ValueError("target_mem must be uint8[batch, %d, 32, 256]" % banks)
+    if source_packed.shape == (32, 128):
+        stride = 0
+    elif tuple(source_packed.shape) == (batch, 32, 128):
+        stride = 4096
+    else:
+        raise ValueError("source_packed must be int64[batch, 32, 128] or [32, 128]")
+    if priority is not None and (priority.dtype != torch.int32
+                                 or tuple(priority.shape) != (batch, banks, 32, 256)):
+        raise ValueError("priority must be int32[batch, %d, 32, 256]" % banks)
+    dev = target_mem.device
+    tpacked = (torch.empty((batch, 32, 128), dtype=torch.int64, device=dev)
+               if want_packed else None)
+    diff = (torch.empty((batch, banks, 32, 256), dtype=torch.int32, device=dev)
+            if want_diff else None)
+    base = _ptr(target_mem)
+    check(lib.iiv_score_frames(
+        m, _ptr(source_packed), stride, base, (base + 8192) if banks == 2 else None,
+        banks * 8192, _ptr(table), _ptr(tpacked) if want_packed else None,
+        _ptr(diff) if want_diff else None, _ptr(priority) if priority is not None else None,
+        int(bool(zero_holes)), batch, _stream()))
+    return tpacked, diff
+
+
 def diff_weights_page(mode, is_aux, source_rows: torch.Tensor,
                       target_rows: torch.Tensor, table: torch.Tensor,
                       content: int = None) -> torch.Tensor:
@@ -344,6 +383,26 @@ def state_field(states: torch.Tensor, field: int, dtype, shape) -> torch.Tensor:
 
 
 F_PACKED, F_MAIN, F_AUX, F_PRIO_MAIN, F_PRIO_AUX, F_MT_NP, F_MT_PY, F_FLAGS = range(8)
+
+
+def seed_clip_states(states: torch.Tensor, seeds) -> torch.Tensor:
+    """``random.seed(s); np.random.seed(s)`` for every clip: both MT19937 fields of clip k
+    are set to the states those calls leave behind (init_by_array / init_genrand)."""
+    import random
+    n = states.shape[0]
+    seeds = list(seeds)
+    if len(seeds) != n:
+        raise ValueError("need one seed per clip")
+    mt_np = np.zeros((n, 640), dtype=np.uint32)
+    mt_py = np.zeros((n, 640), dtype=np.uint32)
+    for k, s in enumerate(seeds):
+        mt_py[k, :625] = mt_from_python(random.Random(int(s)).getstate())
+        mt_np[k, :625] = mt_from_numpy(np.random.RandomState(int(s)).get_state())
+    state_field(states, F_MT_NP, torch.int32, (640,)).copy_(
+        torch.from_numpy(mt_np.view(np.int32)).to(states.device))
+    state_field(states, F_MT_PY, torch.int32, (640,)).copy_(
+        torch.from_numpy(mt_py.view(np.int32)).to(states.device))
+    return states
 
 
 class SegmentPlan:

@@ -69,3 +69,39 @@ def movie_schedule(mode: str, n_frames: int, opcodes_per_frame: int = 980,
             if mode == "DHGR" and count % flip_every == 0:
                 aux = not aux
     return segs
+
+
+# ---- BASELINE.json configs[3] / configs[4]: the scorer's named workloads -------------------
+# (shared by bench.py, the tests and oracle/make_golden.py so that the committed reference
+# hashes describe exactly what is timed)
+
+LONG_CLIP = {"mode": "DHGR", "n_frames": 6000, "fraction": 1.0, "frame_seed": 5,
+             "rng_seed": 0, "golden_frames": 600}
+BATCH_CLIPS = {"mode": "DHGR", "n_clips": 64, "n_frames": 32, "fraction": 1.0,
+               "golden_clips": (0, 9, 18, 27, 36, 45, 54, 63)}
+
+
+def long_clip_frames(n_frames: int = None) -> np.ndarray:
+    """configs[3]: the 6000-frame 560x192 main+aux DHGR clip (every frame re-draws every
+    non-hole byte).  The generator is sequential, so a shorter call returns a prefix."""
+    c = LONG_CLIP
+    return synthetic_frames(c["mode"], n_frames or c["n_frames"], c["fraction"],
+                            seed=c["frame_seed"])
+
+
+def batch_clip_seeds(clip: int):
+    """configs[4]: (frame seed, RNG seed) of clip number ``clip`` of the 64."""
+    return 1000 + clip, 100 + clip
+
+
+def batch_clip_frames(clip: int, n_frames: int = None) -> np.ndarray:
+    c = BATCH_CLIPS
+    return synthetic_frames(c["mode"], n_frames or c["n_frames"], c["fraction"],
+                            seed=batch_clip_seeds(clip)[0])
+
+
+def opcode_digest(opcodes6: np.ndarray) -> str:
+    """SHA-256 of an opcode stream as uint8[n][6] = (page + 32, content, 4 offsets)."""
+    import hashlib
+    a = np.ascontiguousarray(np.asarray(opcodes6)[:, :6], dtype=np.uint8)
+    return hashlib.sha256(a.tobytes()).hexdigest()

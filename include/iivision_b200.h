@@ -154,6 +154,24 @@ int iiv_diff_weights(int mode, int is_aux, const uint64_t* d_source_packed,
                      const uint16_t* d_table, int32_t* d_out, int batch,
                      void* stream);
 
+/* The scoring prologue of Video._index_changes (video.py:109-116) for a batch of frames in
+ * one launch, fused with Bitmap._pack of each target (screen.py:207-226) and covering both
+ * banks of a DHGR frame:
+ *   target_packed = _pack(target memory)
+ *   diff[bank]    = target.diff_weights(source, bank)          (screen.py:400-449)
+ *   diff[bank][SCREEN_HOLES] = 0            if zero_holes       (video.py:111)
+ *   priority[bank][diff == 0] = 0; priority[bank] += diff       (video.py:115-116)
+ * d_source_packed uint64[batch][32][128] with source_stride words between frames (0 = one
+ * source bitmap for every frame); d_target_main / d_target_aux uint8[32][256] per frame,
+ * mem_stride bytes apart (aux NULL for HGR); d_target_packed uint64[batch][32][128] (may be
+ * NULL); d_diff and d_priority int32[batch][banks][32][256], banks = 1 (HGR) / 2 (DHGR:
+ * main, aux); either may be NULL.  d_priority is read and written in place. */
+int iiv_score_frames(int mode, const uint64_t* d_source_packed, size_t source_stride,
+                     const uint8_t* d_target_main, const uint8_t* d_target_aux,
+                     size_t mem_stride, const uint16_t* d_table,
+                     uint64_t* d_target_packed, int32_t* d_diff, int32_t* d_priority,
+                     int zero_holes, int batch, void* stream);
+
 /* Bitmap._diff_weights_page (screen.py:453-494) on n_rows rows of 128 words:
  * d_out int32[n_rows][256]. */
 int iiv_diff_weights_page(int mode, int is_aux, const uint64_t* d_source_rows,

@@ -24,6 +24,9 @@ The reference cannot travel to the GPU box, so its outputs do, as fixtures:
   movie_<case>.npz     the byte stream of the whole Movie.encode + Movie.emit_stream loop
                        (movie.py:56-161) on synthetic frames and audio ticks, with the
                        final encoder state
+  long_streams.json    SHA-256 of the opcode streams of BASELINE.json configs[3] (600-frame
+                       prefix of the 6000-frame DHGR clip) and configs[4] (8 of the 64
+                       clips) from the reference Video.encode_frame; --long-only, minutes
   luts.json            int(dE2000) substitution matrices from oracle/cie2000.py
                        (restated colormath; NOT reference output -- the reference
                        generator cannot run offline) together with the rows
@@ -341,6 +344,79 @@ def gen_movie(ns, case, table):
     print("  %s: %d bytes, %d ticks" % (name, len(data), m.ticks))
 
 
+def _long_worker(job):
+    """One clip through the UNMODIFIED reference Video.encode_frame under the Movie.encode
+    schedule; returns cumulative SHA-256 digests of the opcode stream at checkpoints."""
+    import hashlib
+    kind, clip, n_frames, checkpoints = job
+    ns = ref_harness.load()
+    table = symmetric_table("DHGR")
+    ref_harness.install_tables(ns, "DHGR", {5: table})
+    if kind == "long":
+        frames = synth.long_clip_frames(n_frames)
+        seed = synth.LONG_CLIP["rng_seed"]
+    else:
+        frames = synth.batch_clip_frames(clip, n_frames)
+        seed = synth.batch_clip_seeds(clip)[1]
+    segs = synth.movie_schedule("DHGR", n_frames)
+    vm = ns.video_mode.VideoMode.DHGR
+    random.seed(seed)
+    np.random.seed(seed)
+    v = ns.video.Video(ns.frame_grabber.FrameGrabber(vm), ticks_per_second=14700.,
+                       mode=vm, palette=ns.palette.Palette.NTSC)
+    h = hashlib.sha256()
+    digests = {}
+    import time
+    t0 = time.perf_counter()
+    last_frame = 0
+    for frame, is_aux, budget in segs:
+        if frame != last_frame:
+            if frame in checkpoints:
+                digests[str(frame)] = h.hexdigest()
+            last_frame = frame
+        tgt = ref_bitmap(ns, "DHGR", frames[frame, 0].copy(), frames[frame, 1].copy())
+        seq = v.encode_frame(tgt, bool(is_aux))
+        buf = bytearray()
+        for _ in range(budget):
+            page, content, offs = next(seq)
+            buf += bytes([int(page), int(content)] + [int(o) for o in offs])
+        h.update(bytes(buf))
+    digests[str(n_frames)] = h.hexdigest()
+    dt = time.perf_counter() - t0
+    state = hashlib.sha256()
+    for a in (v.pixelmap.packed, v.memory_map.page_offset, v.aux_memory_map.page_offset,
+              v.update_priority.astype(np.int32), v.aux_update_priority.astype(np.int32)):
+        state.update(np.ascontiguousarray(a).tobytes())
+    return {"kind": kind, "clip": clip, "n_frames": n_frames, "opcode_sha256": digests,
+            "state_sha256": state.hexdigest(), "reference_frames_per_s": n_frames / dt,
+            "next_python_word": int(random.getrandbits(32)),
+            "next_numpy_byte": int(np.random.randint(0, 256))}
+
+
+def gen_long_hashes():
+    """BASELINE.json configs[3] (prefix of the 6000-frame DHGR clip) and configs[4] (8 of
+    the 64 clips): SHA-256 of the opcode streams the unmodified reference emits, one
+    process per clip (the reference is single-threaded, video.py:121-187)."""
+    import multiprocessing as mp
+    lc, bc = synth.LONG_CLIP, synth.BATCH_CLIPS
+    jobs = [("long", -1, lc["golden_frames"], (1, 3, 10, 30, 100, 300))]
+    jobs += [("batch", c, bc["n_frames"], (1, 4, 16)) for c in bc["golden_clips"]]
+    with mp.get_context("spawn").Pool(min(len(jobs), os.cpu_count() or 1)) as pool:
+        res = pool.map(_long_worker, jobs, chunksize=1)
+    out = {"source": "unmodified reference Video.encode_frame (video.py:72-301) under "
+                     "synth.movie_schedule (980 opcodes/frame, bank flip every 292), NTSC, "
+                     "oracle tables; digest = sha256 of uint8[n][6] (page+32, content, 4 "
+                     "offsets), cumulative at the frame counts given",
+           "long_clip": dict(lc), "batch_clips": {k: (list(v) if isinstance(v, tuple) else v)
+                                                  for k, v in bc.items()},
+           "long": res[0], "batch": {str(r["clip"]): r for r in res[1:]}}
+    with open(os.path.join(GOLDEN, "long_streams.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    for r in res:
+        print("  %s %d: %d frames at %.2f frames/s" % (
+            r["kind"], r["clip"], r["n_frames"], r["reference_frames_per_s"]))
+
+
 def gen_luts():
     survey_row0 = {
         "5": [0, 35, 37, 50, 38, 39, 55, 64, 31, 53, 39, 65, 66, 78, 86, 99],
@@ -361,6 +437,9 @@ def gen_luts():
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--long-only" in sys.argv:
+        print("long streams"); gen_long_hashes()
+        return
     ns = ref_harness.load()
     print("helpers"); gen_helpers(ns)
     print("byte stream"); gen_byte_stream(ns)
