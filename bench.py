@@ -22,8 +22,16 @@ array delivered (the same count for every arm and layout).
              on all host cores over a bounded sample of row blocks
   scorer     secondary figures for the second hot path (DHGR frames/s), N=1 only
 
-N > 1: rows shard across ranks (strong scaling: one table, N GPUs) and an in-place
-NCCL all-gather leaves the whole table on every GPU.
+N > 1 (one process per GPU):
+  value      the table resident on EVERY GPU, as the per-GPU scorers need it: each rank
+             generates its own replica, no collective (one GPU makes the table faster
+             than NVLink can deliver (N-1)/N of it); entries counted per replica
+  e2e        ONE host array: rows shard over the ranks, every rank copies its block into
+             its page-locked, NUMA-local slice of a shared host array over its own PCIe
+             link (parallel.compute_edit_distance_sharded)
+  alt_exchange   sharded generation + NVLink exchange (peer stores / multicast / NCCL
+             all-gather), each checked against the local replica
+  scorer     BASELINE.json configs[4]: 64 distinct clips sharded clip-per-GPU
 """
 
 import argparse
@@ -123,7 +131,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (palette constants; no external data)",
         "config": workload_config(args.gpus),
         "cpu_baseline": {
@@ -138,22 +146,21 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus, exchange="fused_peer"):
-    how = ""
-    if n_gpus > 1:
-        how = {"nccl": " + in-place NCCL all-gather",
-               "fused_peer": " + exchange fused into the generator (stores to every "
-                             "rank's peer-mapped table over NVLink)",
-               "fused_mc": " + exchange fused into the generator (multimem.st through "
-                           "the NVSwitch multicast mapping)"}[exchange]
+def workload_config(n_gpus):
     return {
         "workload": "HGR NTSC edit-distance table (make_data_tables.compute_edit_distance): "
                     "2 offsets x 2^28 uint16 entries = 1 GiB, 18-pixel strings",
         "layout": "symmetric (Bitmap.edit_distances form) for value; reference "
                   "lower-triangular array for e2e",
-        "entries_per_step": ENTRIES,
-        "l2": "each step writes 1 GiB (> 126 MB L2); no explicit flush",
-        "parallelism": "rows sharded over %d GPU(s)%s" % (n_gpus, how),
+        "entries_per_step": ENTRIES * n_gpus,
+        "l2": "each step writes 1 GiB per GPU (> 126 MB L2); no explicit flush",
+        "parallelism": (
+            "one GPU" if n_gpus == 1 else
+            "value: the table resident on every GPU (what the per-GPU scorers gather from) = "
+            "%d replicas, each rank generates its own, no collective; entries counted per "
+            "replica (weak scaling).  e2e: ONE host array, rows sharded over the %d ranks, "
+            "each rank copies its block home over its own PCIe link.  alt_exchange: sharded "
+            "generation + NVLink exchange variants, slower than replicas" % (n_gpus, n_gpus)),
     }
 
 
@@ -660,49 +667,47 @@ def run_ours(args, rank, world, local_rank):
     if args.scorer_only:
         print(json.dumps({"scorer": scorer_figures(torch, ops)}))
         return
+    # one process per GPU: keep the process (and every page it first touches or page-locks)
+    # on the NUMA node its GPU hangs off
+    numa_node = parallel.bind_to_gpu_numa_node(local_rank) if world > 1 else None
     pal = palette.NTSCPalette
     edp = make_data_tables.compute_substitute_costs(pal)       # LUT on the device (FP64)
     lut = make_data_tables._lut16(edp.substitute_costs)
     table = torch.empty(ops.table_shape(MODE), dtype=torch.uint16, device="cuda")
     stream = torch.cuda.current_stream()
 
-    exchange = os.environ.get("IIV_EXCHANGE", "fused_peer")   # fused_peer | fused_mc | nccl
-
     def sharded_step(how):
         if how == "nccl":
-            parallel.generate_sharded(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
-        else:
-            parallel.generate_sharded_fused(MODE, lut, layout=ops.LAYOUT_SYMMETRIC,
-                                            multicast=(how == "fused_mc"))
+            return parallel.generate_sharded(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=xtable)
+        return parallel.generate_sharded_fused(MODE, lut, layout=ops.LAYOUT_SYMMETRIC,
+                                               multicast=(how == "fused_mc"))
 
     def step():
-        if world == 1:
-            ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
-        else:
-            sharded_step(exchange)
+        # N = 1: the table.  N > 1: the table on EVERY GPU, which is what the scorer needs
+        # (each clip's encoder gathers from its own GPU's copy): every rank generates its
+        # own replica.  One GPU makes the table (0.26 ms) faster than NVLink can deliver
+        # (N-1)/N of it (>= 1.2 ms at 8 GPUs), so replicas beat any exchange; the sharded
+        # variants are timed below as alt_exchange.
+        ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    exchange_note = None
-    if world > 1 and exchange != "nccl":
-        # symmetric (peer-mapped) memory needs NVLink P2P between all ranks; if the
-        # rendezvous fails on this box every rank falls back to the NCCL all-gather
-        ok = 1
-        try:
-            sharded_step(exchange)
-            torch.cuda.synchronize()
-        except Exception as e:   # noqa: BLE001
-            ok = 0
-            exchange_note = "fused exchange unavailable (%s); NCCL all-gather used" % (
-                str(e).splitlines()[0][:120])
-        flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if not int(flag.item()):
-            exchange = "nccl"
-            exchange_note = exchange_note or "fused exchange unavailable on another rank"
+    def allmax(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allmin_int(x):
+        if world == 1:
+            return int(x)
+        t = torch.tensor([int(x)], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.3 if rank == 0 else 0)
@@ -732,105 +737,111 @@ def run_ours(args, rank, world, local_rank):
         evs[k + 1].record(stream)
     barrier()
     t_host1 = time.perf_counter()
-    total_ms = evs[0].elapsed_time(evs[-1])
     per_step = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
+    total_ms = allmax(evs[0].elapsed_time(evs[-1]))
+    # every rank delivered one whole table per step
+    value = world * ENTRIES * args.steps / (total_ms * 1e-3)
+
+    # outside the timed region: the replicas are the same table everywhere
+    replicas_identical = None
     if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    value = ENTRIES * args.steps / (total_ms * 1e-3)
+        sig = torch.stack([table.view(torch.int32).sum(dtype=torch.int64),
+                           table.view(torch.int32)[::4097].sum(dtype=torch.int64)])
+        sigs = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(sigs, sig)
+        replicas_identical = all(bool(torch.equal(x, sigs[0])) for x in sigs)
 
     alt = None
     if world > 1:
-        # the other exchanges, for the record (same K, same barriers)
+        # sharded generation + exchange (rows split over the ranks, every rank ends up with
+        # the whole table), same K and barriers; each result is compared with this rank's
+        # own replica outside the timed region
         alt = []
-        for other in ("fused_peer", "fused_mc", "nccl"):
-            if other == exchange:
-                continue
+        xtable = torch.empty_like(table)
+        for how in ("fused_peer", "fused_mc", "nccl"):
+            ok = 1
+            res = None
             try:
                 for _ in range(3):
-                    sharded_step(other)
+                    res = sharded_step(how)
+                torch.cuda.synchronize()
             except Exception as e:          # e.g. no multicast on this fabric  # noqa: BLE001
-                alt.append({"exchange": other, "unavailable": str(e).splitlines()[0][:80]})
+                ok = 0
+                err = str(e).splitlines()[0][:80]
+            if not allmin_int(ok):
+                alt.append({"exchange": how, "unavailable": err if not ok else "on another rank"})
                 continue
             barrier()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record(stream)
             for _ in range(args.steps):
-                sharded_step(other)
+                res = sharded_step(how)
             a1.record(stream)
             barrier()
-            t = torch.tensor([a0.elapsed_time(a1)], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            alt.append({"exchange": other, "ms_per_step": float(t.item()) / args.steps,
-                        "value": ENTRIES * args.steps / (float(t.item()) * 1e-3)})
-        # and no exchange at all: every rank generates the whole table for itself.  One GPU
-        # makes the table faster than NVLink can deliver (N-1)/N of it, so this is the
-        # quickest way to have it on every GPU; listed for reference, not the headline.
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record(stream)
-        for _ in range(args.steps):
-            ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
-        a1.record(stream)
-        barrier()
-        t = torch.tensor([a0.elapsed_time(a1)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        alt.append({"exchange": "none (replicated: each rank generates all rows)",
-                    "ms_per_step": float(t.item()) / args.steps,
-                    "value": ENTRIES * args.steps / (float(t.item()) * 1e-3)})
+            ms = allmax(a0.elapsed_time(a1)) / args.steps
+            same = allmin_int(int(torch.equal(res.view(torch.int16), table.view(torch.int16))))
+            alt.append({"exchange": how, "ms_per_step": ms,
+                        "tables_per_s_whole_job": 1e3 / ms,
+                        "entries_per_s_one_table": ENTRIES / (ms * 1e-3),
+                        "equals_local_replica_on_every_rank": bool(same)})
+        del xtable
 
-    # kernel-only timing for the roofline: the generator kernel(s) of this rank's rows
-    rows = parallel.row_partition(1 << BITS, world)[rank]
+    # kernel-only timing for the roofline: the generator kernel of this rank's table
     kev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     kernel_ms = []
     for _ in range(min(args.steps, 10)):
         kev[0].record(stream)
-        ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, row_begin=rows[0],
-                           row_end=rows[1], out=table)
+        ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
         kev[1].record(stream)
         torch.cuda.synchronize()
         kernel_ms.append(kev[0].elapsed_time(kev[1]))
-    # clocks over warm-up + timed region + the kernel-only loop (all back-to-back
-    # generator launches); the timed region alone can be shorter than one sample
-    # reference point: a plain fill of the same buffer (write-only stream).  HBM3e takes
-    # writes slower than the read+write mix of the copy that MEASURED_PEAKS.json records
-    fill_ms = []
-    tbl16 = table.view(torch.int16)
-    for _ in range(12):
-        kev[0].record(stream)
-        tbl16.fill_(7)
-        kev[1].record(stream)
-        torch.cuda.synchronize()
-        fill_ms.append(kev[0].elapsed_time(kev[1]))
-    fill_ms = sorted(fill_ms[2:])[len(fill_ms[2:]) // 2]
-    fill_gbs = 2.0 * ENTRIES / (fill_ms * 1e-3) / 1e9
+    # reference points: write-only streams over the same 1 GiB buffer.  cudaMemsetAsync and
+    # a one-store-per-thread fill reach 7.2-7.4 TB/s on this part (profiles/r02_hbm_fill.txt)
+    # -- above the read+write copy figure MEASURED_PEAKS.json records; torch's fill_ kernel
+    # does not (3.9 TB/s) and is no ceiling.
+    fill_gbs = {}
+    for name, variant in (("memset", 0), ("one_store_per_thread", 1)):
+        ts = []
+        for _ in range(12):
+            kev[0].record(stream)
+            ops.fill_probe(table, variant)
+            kev[1].record(stream)
+            torch.cuda.synchronize()
+            ts.append(kev[0].elapsed_time(kev[1]))
+        ts = sorted(ts[2:])
+        fill_gbs[name] = 2.0 * ENTRIES / (ts[len(ts) // 2] * 1e-3) / 1e9
+    ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
     clocks = sampler.summary(t_load0, time.perf_counter()) if sampler else None
     k_ms = sum(kernel_ms) / len(kernel_ms)
     peaks, peak_src = measured_peaks()
-    alg_bytes = 2.0 * ENTRIES / world
+    alg_bytes = 2.0 * ENTRIES
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
 
-    # e2e through the reference-facing call: host in, host numpy out
+    # e2e through the reference-facing call: host parameters in, host numpy array out
     e2e_steps = max(2, min(args.steps, 5))
-    shard = (rows[1] - rows[0]) * (1 << BITS) * N_OFF * 2
+    # bytes one rank's banded lower-triangle download moves (ops.table_download)
+    d2h_bytes = 0
+    for b, e in parallel.triangle_row_blocks(1 << BITS, world, rank):
+        per = -(-(e - b) // ops.DOWNLOAD_BANDS)
+        for r0 in range(b, e, per):
+            r1 = min(r0 + per, e)
+            d2h_bytes += N_OFF * (r1 - r0) * min((2 * (r1 - 1) + 63) // 64 * 64, 2 << BITS)
+    host = None
     if world == 1:
         def e2e_step():
             edp_ = make_data_tables.compute_substitute_costs(pal)
             return make_data_tables.compute_edit_distance(
                 edp_, screen.HGRBitmap, colours.HGRColours)
     else:
-        host = torch.empty((N_OFF, (rows[1] - rows[0]) << BITS), dtype=torch.uint16,
-                           pin_memory=True)
+        host = parallel.SharedHostTable(MODE)
 
         def e2e_step():
-            # every rank generates its row block and copies only that block home
-            ops.table_generate(MODE, lut, layout=ops.LAYOUT_TRIANGULAR, row_begin=rows[0],
-                               row_end=rows[1], out=table)
-            view = table.view(N_OFF, 1 << BITS, 1 << BITS)[:, rows[0]:rows[1]]
-            host.view(N_OFF, rows[1] - rows[0], 1 << BITS).copy_(view, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return host
+            # every rank: LUT (device FP64), its row block, its own D2H into its page-locked
+            # slice of the one shared host array; rank 0's caller holds the array
+            edp_ = make_data_tables.compute_substitute_costs(pal)
+            return parallel.compute_edit_distance_sharded(
+                MODE, make_data_tables._lut16(edp_.substitute_costs), host,
+                device_table=table)
     e2e_step()
     barrier()
     res = None
@@ -839,25 +850,40 @@ def run_ours(args, rank, world, local_rank):
         res = None          # the caller drops one table before asking for the next
         res = e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_verified = None
     if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        # rank 0 checks the assembled host array against a table it generates alone
+        if rank == 0:
+            ops.table_generate(MODE, lut, layout=ops.LAYOUT_TRIANGULAR, out=table)
+            e2e_verified = bool(np.array_equal(
+                res, table.cpu().view(torch.int16).numpy().view(np.uint16)))
+        barrier()
     # the e2e step is the device-to-host copy of the table: time that copy alone, same
     # page-locked destination, so the figure can be read against this box's PCIe rate
-    d2h_ms = None
+    d2h_ms = d2h_full_ms = None
     if world == 1 and res is not None:
-        dst = torch.from_numpy(res)
+        del res
+        res = None
+        # the bare copies next to it: the banded lower-triangle download the call uses, and
+        # a whole-table copy (what moving the zeros too would cost) -- same page-locked pool
+        lease, arr = make_data_tables._pinned_pool.lease(tuple(table.shape))
+        ops.table_generate(MODE, lut, layout=ops.LAYOUT_TRIANGULAR, out=table)
         evc = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        if dst.is_pinned():
-            evc[0].record()
-            dst.view(torch.int16).copy_(table.view(torch.int16).view(dst.shape), non_blocking=True)
-            evc[1].record()
-            torch.cuda.synchronize()
-            d2h_ms = evc[0].elapsed_time(evc[1])
-        del dst
+        evc[0].record()
+        ops.table_download(MODE, table, lease.data_ptr(), layout=ops.LAYOUT_TRIANGULAR)
+        evc[1].record()
+        torch.cuda.synchronize()
+        d2h_ms = evc[0].elapsed_time(evc[1])
+        evc[0].record()
+        ops.table_download(MODE, table, lease.data_ptr(), layout=ops.LAYOUT_SYMMETRIC)
+        evc[1].record()
+        torch.cuda.synchronize()
+        d2h_full_ms = evc[0].elapsed_time(evc[1])
+        del arr, lease
     del res
+    if host is not None:
+        host.close()
     if sampler:
         sampler.stop()
 
@@ -870,45 +896,57 @@ def run_ours(args, rank, world, local_rank):
                                          dist=dist)
         except Exception as e:   # noqa: BLE001
             clips_multi = {"error": repr(e)}
+    nodes = None
+    if world > 1:
+        nodes = [None] * world
+        dist.all_gather_object(nodes, numa_node)
     if rank != 0:
         return
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3, done),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u16",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u16",
         "data": "synthetic (palette constants; no external data)",
-        "config": dict(workload_config(world, exchange),
-                       **({"exchange_note": exchange_note} if exchange_note else {})),
+        "config": workload_config(world),
         "clocks": clocks,
         "e2e": {"value": ENTRIES * e2e_steps / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": 16 * 3 + 256 * 4,
-                "d2h_bytes_per_step": (2 * ENTRIES if world == 1 else shard) + 256 * 4,
+                "d2h_bytes_per_step": d2h_bytes + 256 * 4,
                 "steps": e2e_steps,
-                **({"d2h_copy_ms": d2h_ms,
-                    "d2h_copy_gbs": 2.0 * ENTRIES / (d2h_ms * 1e-3) / 1e9} if d2h_ms else {}),
+                **({"d2h_copy_ms": d2h_ms, "d2h_whole_table_copy_ms": d2h_full_ms,
+                    "d2h_whole_table_copy_gbs": 2.0 * ENTRIES / (d2h_full_ms * 1e-3) / 1e9}
+                   if d2h_ms else {}),
+                **({"assembled_array_equals_single_gpu_table": e2e_verified,
+                    "gpu_numa_nodes": nodes} if world > 1 else {}),
                 "call": "make_data_tables.compute_substitute_costs + compute_edit_distance "
-                        "-> host uint16 array" if world == 1 else
-                        "per-rank row block generate + D2H of that block"},
+                        "-> host uint16 array (only j < i crosses PCIe: the array's other "
+                        "half is zero by construction)" if world == 1 else
+                        "compute_substitute_costs + parallel.compute_edit_distance_sharded: ONE "
+                        "host uint16 array (the reference's lower-triangular table) in shared "
+                        "page-locked memory; each rank generates its row block and copies it "
+                        "over its own PCIe link; d2h bytes are per rank"},
         "gpu_launches": ops.launches_per_table_generate() * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                     "traffic": ncu_traffic() if world == 1 else None,
+                     "traffic": ncu_traffic(),
                      "peak_source": peak_src, "kernel": ops.generator_kernel_name(),
                      "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "write_only_fill_gbs": fill_gbs,
-                     "frac_of_write_only_fill": achieved / fill_gbs,
+                     "write_only_gbs": fill_gbs,
+                     "frac_of_write_only": achieved / max(fill_gbs.values()),
                      "note": "2 B stored per entry x entries per launch / CUDA-event "
                              "time of the generate call on its stream; peak = measured "
-                             "copy (read+write) bandwidth; write_only_fill_gbs = torch "
-                             "fill_ of the whole 1 GiB table timed in this run: a "
-                             "write-only stream tops out there, and the generator "
-                             "stores every byte exactly once and reads nothing"},
+                             "copy (read+write) bandwidth; write_only_gbs = "
+                             "cudaMemsetAsync and a one-16-byte-store-per-thread kernel over "
+                             "the same 1 GiB timed in this run, the write-only ceiling "
+                             "(profiles/r02_hbm_fill.txt): the generator stores every byte "
+                             "exactly once and reads nothing"},
         "step_ms_min_max": [min(per_step), max(per_step)],
         "wall_s_timed_region": t_host1 - t_host0,
     }
-    if alt is not None:
+    if world > 1:
+        line["replicas_identical"] = replicas_identical
         line["alt_exchange"] = alt
     if world == 1:
         # the reference's whole job (README "about 90 minutes"): both modes x both palettes

@@ -24,6 +24,9 @@ c_u32, c_u8 = ctypes.c_uint32, ctypes.c_uint8
 PROTOTYPES = {
     "iiv_last_error": (ctypes.c_char_p, []),
     "iiv_version": (c_int, []),
+    "iiv_set_l2_fetch_granularity": (c_int, [c_size_t]),
+    "iiv_get_l2_fetch_granularity": (c_size_t, []),
+    "iiv_fill_probe": (c_int, [c_void_p, c_size_t, c_int, c_void_p]),
     "iiv_mode_info": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "iiv_lut_cie2000": (c_int, [c_void_p, c_void_p]),
     "iiv_lut_cie2000_f64": (c_int, [c_void_p, c_void_p]),
@@ -34,6 +37,8 @@ PROTOTYPES = {
     "iiv_table_generate_scatter": (c_int, [c_int, c_void_p, c_void_p, c_int,
                                            c_int, c_void_p, c_u32, c_u32, c_int,
                                            c_void_p]),
+    "iiv_table_download": (c_int, [c_int, c_void_p, c_void_p, c_u32, c_u32, c_int, c_int,
+                                   c_void_p]),
     "iiv_table_symmetrise": (c_int, [c_int, c_void_p, c_void_p]),
     "iiv_pack": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_int,
                          c_void_p]),

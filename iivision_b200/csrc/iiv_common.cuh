@@ -183,6 +183,16 @@ __host__ __device__ __forceinline__ uint32_t nominal_pixel(uint32_t dots, int t,
   return ((w << ph) | (w >> (4 - ph))) & 0xfu;
 }
 
+// One entry of an edit-distance table (the scorer's random 2-byte gathers, screen.py:441,
+// :486).  Read-only path; the L2::64B hint measured 5 % more gathers/s than a plain
+// ld.global.nc on uniformly random indices over the 512 MiB DHGR table
+// (profiles/r02_gather_flavours.txt) -- DRAM moves ~107 B per missing gather either way.
+__device__ __forceinline__ uint32_t ldg_table(const uint16_t* p) {
+  uint16_t v;
+  asm("ld.global.nc.L2::64B.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+
 // ---- MT19937 (numpy legacy RandomState and CPython random share it) --------
 __host__ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   y ^= y >> 11;

@@ -49,8 +49,10 @@ constexpr int kRing = 16;               // prefetched delta rows in flight
 constexpr int kPyBlocks = 4;            // resident 624-word blocks of stream P (power of 2)
 constexpr int kCells = 32 * 256;       // one bank: 32 pages x 256 offsets
 constexpr int kCols = 32 * 128;
-constexpr int kPushedCap = 4096;       // >= 2 * max budget per segment
-constexpr int kMaxBudget = kPushedCap / 2;
+constexpr int kPushedCap = 4096;       // re-queued cells kept in shared memory; a segment of
+                                       // more than kPushedCap / 2 opcodes may overflow into
+                                       // a per-clip scratch list in global memory
+constexpr int kMaxBudget = 1 << 17;    // opcodes per segment (one encode_frame generator)
 constexpr uint64_t kDead = ~0ull;
 
 // Offsets of the fields inside a clip state blob (bytes).
@@ -228,7 +230,7 @@ __device__ __forceinline__ uint4 score_row_regs(const uint64_t* __restrict__ tp_
         const uint32_t x = mask_shift<MODE>(masked_update<MODE>(o, w[q], content), o);
         const uint32_t y = mask_shift<MODE>(w[q], o);
         nd[2 * q + half] =
-            __ldg(table + ((size_t)o << (2 * M::kBits)) + ((size_t)x << M::kBits) + y);
+            ldg_table(table + ((size_t)o << (2 * M::kBits)) + ((size_t)x << M::kBits) + y);
       }
     packed_out = make_uint4(nd[0] | (nd[1] << 16), nd[2] | (nd[3] << 16),
                             nd[4] | (nd[5] << 16), nd[6] | (nd[7] << 16));
@@ -321,7 +323,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
               const uint64_t* __restrict__ target_packed, int n_frames,
               const int32_t* __restrict__ segments, int n_segments,
               const uint16_t* __restrict__ table, uint8_t* __restrict__ opcodes,
-              int64_t total_budget, int64_t* __restrict__ seg_info) {
+              int64_t total_budget, int64_t* __restrict__ seg_info,
+              uint64_t* __restrict__ overflow, int overflow_cap) {
   using M = Mode<MODE>;
   constexpr int kBanks = MODE == IIV_MODE_DHGR ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -362,6 +365,11 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
   int error_flags = 0;
 
   uint8_t* op_out = opcodes + (size_t)clip * total_budget * 8;
+  // re-queued cells beyond the shared-memory list (only segments of more than
+  // kPushedCap / 2 opcodes can get there): written and read by the decision warp alone
+  volatile uint64_t* const ovf =
+      overflow != nullptr ? overflow + (size_t)clip * (size_t)overflow_cap : nullptr;
+  const int pushed_cap = kPushedCap + (ovf != nullptr ? overflow_cap : 0);
 
   for (int seg = 0; seg < n_segments; ++seg) {
     const int frame = segments[3 * seg + 0];
@@ -408,7 +416,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         }
       }
 #pragma unroll
-      for (int k = 0; k < 32; ++k) dwv[k] = __ldg(table + gidx[k]);
+      for (int k = 0; k < 32; ++k) dwv[k] = ldg_table(table + gidx[k]);
 #pragma unroll
       for (int k = 0; k < 32; ++k)
         if (is_hole((t & 7) * 32 + k)) dwv[k] = 0;   // video.py:111
@@ -857,11 +865,21 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         if (heap_done) {
           // first-pass heap exhausted: arg-min over live re-queued cells, scored on demand
           uint64_t best = kDead;
-          for (int k = lane; k < n_pushed; k += 32) {
+          const int n_shared = min(n_pushed, kPushedCap);
+          for (int k = lane; k < n_shared; k += 32) {
             const uint64_t key = sm.pushed[k];
             if (key == kDead) continue;
             if (sm.prio[key & 0x1fffu] == 0) {
               sm.pushed[k] = kDead;  // stale: would be popped and skipped
+              continue;
+            }
+            best = key < best ? key : best;
+          }
+          for (int k = kPushedCap + lane; k < n_pushed; k += 32) {   // overflow list
+            const uint64_t key = ovf[k - kPushedCap];
+            if (key == kDead) continue;
+            if (sm.prio[key & 0x1fffu] == 0) {
+              ovf[k - kPushedCap] = kDead;
               continue;
             }
             best = key < best ? key : best;
@@ -871,8 +889,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             out_of_work = true;
             break;
           }
-          for (int k = lane; k < n_pushed; k += 32)
+          for (int k = lane; k < n_shared; k += 32)
             if (sm.pushed[k] == best) sm.pushed[k] = kDead;
+          for (int k = kPushedCap + lane; k < n_pushed; k += 32)
+            if (ovf[k - kPushedCap] == best) ovf[k - kPushedCap] = kDead;
           cell = (int)(best & 0x1fffu);
           slot = kRing;
           content = __ldg(tmem + cell);
@@ -953,7 +973,11 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           p2 = sm.ring_row[slot][o2];
         }
         }
-        const int push1 = p1 != 0, push2 = p2 != 0;
+        int push1 = p1 != 0, push2 = p2 != 0;
+        if (n_pushed + push1 + push2 > pushed_cap) {   // the host sizes the overflow list so
+          error_flags |= 4;                            // that this cannot happen
+          push1 = push2 = 0;
+        }
         if (lane == 0) {
           // volatile: these stores must stay ahead of the b_done store below
           volatile int32_t* vprio = sm.prio;
@@ -961,11 +985,18 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           reinterpret_cast<volatile uint16_t*>(sm.dw)[cell] = 0;      // video.py:141
           if (has1) vprio[page * 256 + o1] = (int32_t)p1;            // video.py:170
           if (has2) vprio[page * 256 + o2] = (int32_t)p2;
-          if (push1)   // video.py:173-178
-            sm.pushed[n_pushed] = requeue_key(p1, push_nonce0, page * 256 + o1);
-          if (push2)
-            sm.pushed[n_pushed + push1] =
+          if (push1) {   // video.py:173-178
+            const uint64_t key = requeue_key(p1, push_nonce0, page * 256 + o1);
+            if (n_pushed < kPushedCap) sm.pushed[n_pushed] = key;
+            else ovf[n_pushed - kPushedCap] = key;
+          }
+          if (push2) {
+            const uint64_t key =
                 requeue_key(p2, push1 ? push_nonce1 : push_nonce0, page * 256 + o2);
+            const int at = n_pushed + push1;
+            if (at < kPushedCap) sm.pushed[at] = key;
+            else ovf[at - kPushedCap] = key;
+          }
           // video.py:185-187: pad to 4 with offsets[0]
           uint2 rec;
           rec.x = (uint32_t)(page + 32) | (content << 8) | ((uint32_t)off << 16) |
@@ -1442,42 +1473,61 @@ extern "C" int iiv_clip_state_layout(size_t* offsets8) {
 }
 
 static int check_segments(int mode, int n_frames, const int32_t* h_segments, int n_segments,
-                          int64_t* total_out) {
+                          int64_t* total_out, int* max_budget_out) {
   int64_t total = 0;
+  int max_budget = 0;
   for (int s = 0; s < n_segments; ++s) {
     const int32_t* q = h_segments + 3 * s;
     IIV_REQUIRE(q[0] >= 0 && q[0] < n_frames, "segment %d: frame %d out of range", s, q[0]);
     IIV_REQUIRE(!(q[1] && mode == IIV_MODE_HGR), "segment %d: HGR has no aux bank", s);
     IIV_REQUIRE(q[2] >= 0 && q[2] <= kMaxBudget, "segment %d: budget %d outside 0..%d", s, q[2], kMaxBudget);
     total += q[2];
+    if (q[2] > max_budget) max_budget = q[2];
   }
   *total_out = total;
+  *max_budget_out = max_budget;
   return 0;
 }
+
+static cudaError_t scratch_pool(cudaMemPool_t* out);
 
 static int launch_encode(int mode, int n_clips, uint8_t* d_state, size_t state_stride,
                          const uint8_t* d_target_mem, const uint64_t* d_target_packed,
                          int n_frames, const int32_t* d_segments, int n_segments, int64_t total,
-                         const uint16_t* d_table, uint8_t* d_opcodes, int64_t* d_seg_info,
-                         cudaStream_t st) {
+                         int max_budget, const uint16_t* d_table, uint8_t* d_opcodes,
+                         int64_t* d_seg_info, cudaStream_t st) {
   const size_t smem = sizeof(Smem);
   cudaError_t e;
+  // An opcode re-queues at most two cells (video.py:173-178): a segment of more than
+  // kPushedCap / 2 opcodes gets a per-clip overflow list, stream-ordered scratch from the
+  // library's own pool.
+  uint64_t* d_overflow = nullptr;
+  int overflow_cap = 0;
+  if (2 * (int64_t)max_budget > kPushedCap) {
+    overflow_cap = 2 * max_budget - kPushedCap;
+    cudaMemPool_t pool;
+    IIV_CUDA(scratch_pool(&pool));
+    IIV_CUDA(cudaMallocFromPoolAsync((void**)&d_overflow,
+                                     sizeof(uint64_t) * (size_t)overflow_cap * (size_t)n_clips,
+                                     pool, st));
+  }
   if (mode == IIV_MODE_HGR) {
     e = cudaFuncSetAttribute(encode_kernel<IIV_MODE_HGR>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       encode_kernel<IIV_MODE_HGR><<<n_clips, kThreads, smem, st>>>(
           d_state, state_stride, d_target_mem, d_target_packed, n_frames, d_segments,
-          n_segments, d_table, d_opcodes, total, d_seg_info);
+          n_segments, d_table, d_opcodes, total, d_seg_info, d_overflow, overflow_cap);
   } else {
     e = cudaFuncSetAttribute(encode_kernel<IIV_MODE_DHGR>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       encode_kernel<IIV_MODE_DHGR><<<n_clips, kThreads, smem, st>>>(
           d_state, state_stride, d_target_mem, d_target_packed, n_frames, d_segments,
-          n_segments, d_table, d_opcodes, total, d_seg_info);
+          n_segments, d_table, d_opcodes, total, d_seg_info, d_overflow, overflow_cap);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
+  if (d_overflow) cudaFreeAsync(d_overflow, st);
   if (e != cudaSuccess) return cuda_fail(e, "encode_kernel");
   return 0;
 }
@@ -1536,7 +1586,8 @@ extern "C" int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
   IIV_REQUIRE(h_segments || n_segments == 0, "null pointer");
   if (n_clips == 0 || n_segments == 0) return 0;
   int64_t total = 0;
-  rc = check_segments(mode, n_frames, h_segments, n_segments, &total);
+  int max_budget = 0;
+  rc = check_segments(mode, n_frames, h_segments, n_segments, &total, &max_budget);
   if (rc) return rc;
   IIV_REQUIRE(d_opcodes || total == 0, "null opcode buffer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1549,7 +1600,7 @@ extern "C" int iiv_encode_clips(int mode, int n_clips, uint8_t* d_state,
                                   cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess)
     rc = launch_encode(mode, n_clips, d_state, state_stride, d_target_mem, d_target_packed,
-                       n_frames, d_segments, n_segments, total, d_table, d_opcodes,
+                       n_frames, d_segments, n_segments, total, max_budget, d_table, d_opcodes,
                        d_seg_info, st);
   cudaFreeAsync(d_segments, st);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(segments)");
@@ -1568,12 +1619,13 @@ extern "C" int iiv_encode_clips_planned(int mode, int n_clips, uint8_t* d_state,
   IIV_REQUIRE((h_segments && d_segments) || n_segments == 0, "null pointer");
   if (n_clips == 0 || n_segments == 0) return 0;
   int64_t total = 0;
-  rc = check_segments(mode, n_frames, h_segments, n_segments, &total);
+  int max_budget = 0;
+  rc = check_segments(mode, n_frames, h_segments, n_segments, &total, &max_budget);
   if (rc) return rc;
   IIV_REQUIRE(d_opcodes || total == 0, "null opcode buffer");
   return launch_encode(mode, n_clips, d_state, state_stride, d_target_mem, d_target_packed,
-                       n_frames, d_segments, n_segments, total, d_table, d_opcodes, d_seg_info,
-                       (cudaStream_t)stream);
+                       n_frames, d_segments, n_segments, total, max_budget, d_table, d_opcodes,
+                       d_seg_info, (cudaStream_t)stream);
 }
 
 extern "C" int iiv_mt_draw(uint32_t* d_mt625, uint32_t* d_words, int n, void* stream) {

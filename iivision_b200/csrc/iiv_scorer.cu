@@ -124,8 +124,8 @@ diff_weights_kernel(int is_aux, const uint64_t* __restrict__ src,
     const uint64_t cmp = content >= 0 ? masked_update<MODE>(o, s, (uint32_t)content) : s;
     const uint32_t x = mask_shift<MODE>(cmp, o);
     const uint32_t y = mask_shift<MODE>(t, o);
-    const uint16_t d = __ldg(table + ((size_t)o << (2 * M::kBits)) +
-                             ((size_t)x << M::kBits) + y);
+    const uint16_t d = (uint16_t)ldg_table(table + ((size_t)o << (2 * M::kBits)) +
+                                           ((size_t)x << M::kBits) + y);
     (half ? res.y : res.x) = d;
   }
   reinterpret_cast<int2*>(out)[c] = res;
@@ -218,7 +218,7 @@ score_frames_kernel(const uint64_t* __restrict__ src, size_t src_stride,
 #pragma unroll
   for (int b = 0; b < kBanks; ++b)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) dw[b][k] = (int32_t)__ldg(table + idx[b][k]);
+    for (int k = 0; k < 8; ++k) dw[b][k] = (int32_t)ldg_table(table + idx[b][k]);
   // the priorities stream in while the gathers are in flight
   int4 pin[kBanks][2];
   if (prio != nullptr) {
@@ -272,8 +272,8 @@ delta_page_kernel(int is_aux, const uint64_t* __restrict__ tgt_row, int content,
     const int o = byte_offset<MODE>(half, is_aux);
     const uint32_t x = mask_shift<MODE>(masked_update<MODE>(o, t, (uint32_t)content), o);
     const uint32_t y = mask_shift<MODE>(t, o);
-    const int32_t d = __ldg(table + ((size_t)o << (2 * M::kBits)) +
-                            ((size_t)x << M::kBits) + y);
+    const int32_t d = (int32_t)ldg_table(table + ((size_t)o << (2 * M::kBits)) +
+                                         ((size_t)x << M::kBits) + y);
     (half ? res.y : res.x) = d - (half ? dr.y : dr.x);
   }
   reinterpret_cast<int2*>(out)[c] = res;
@@ -301,8 +301,8 @@ delta_rows_kernel(int is_aux, const uint64_t* __restrict__ tgt,
     const uint32_t x1 = mask_shift<MODE>(masked_update<MODE>(o1, t, content), o1);
     // symmetric table: T[x][y] == T[y][x]; index as (x << bits) + y like the
     // reference (source-with-content in the high half).
-    const uint32_t d0 = __ldg(t0 + ((size_t)x0 << M::kBits));
-    const uint32_t d1 = __ldg(t1 + ((size_t)x1 << M::kBits));
+    const uint32_t d0 = ldg_table(t0 + ((size_t)x0 << M::kBits));
+    const uint32_t d1 = ldg_table(t1 + ((size_t)x1 << M::kBits));
     *reinterpret_cast<uint32_t*>(dst + (size_t)content * 256) = d0 | (d1 << 16);
   }
 }
@@ -318,7 +318,7 @@ __global__ void pair_difference_kernel(int o, const uint64_t* __restrict__ old_p
   const uint64_t w = old_packed[k];
   const uint32_t oldp = mask_shift<MODE>(w, o);
   const uint32_t newp = mask_shift<MODE>(masked_update<MODE>(o, w, content[k]), o);
-  out[k] = __ldg(table + ((size_t)o << (2 * M::kBits)) + ((size_t)oldp << M::kBits) + newp);
+  out[k] = (uint16_t)ldg_table(table + ((size_t)o << (2 * M::kBits)) + ((size_t)oldp << M::kBits) + newp);
 }
 
 struct Stores {

@@ -680,6 +680,43 @@ extern "C" int iiv_string_distance(const int32_t* h_lut, const uint8_t* d_a,
   return 0;
 }
 
+// The device-to-host leg of compute_edit_distance.  In the reference's file layout only
+// j < i can be nonzero (make_data_tables.py:156-172), so moving whole rows would spend half
+// of the PCIe time on zeros: the rows go home in bands, each as one 2-D copy that is only as
+// wide as the band's last row needs.  The rest of the destination is left alone -- the
+// caller hands in a buffer whose other bytes are already zero.
+extern "C" int iiv_table_download(int mode, const uint16_t* d_table, uint16_t* h_table,
+                                  uint32_t row_begin, uint32_t row_end, int layout, int bands,
+                                  void* stream) {
+  IIV_REQUIRE(mode == IIV_MODE_HGR || mode == IIV_MODE_DHGR, "bad mode %d", mode);
+  IIV_REQUIRE(d_table && h_table, "null pointer");
+  IIV_REQUIRE(layout == IIV_LAYOUT_TRIANGULAR || layout == IIV_LAYOUT_SYMMETRIC,
+              "bad layout %d", layout);
+  const uint32_t bits = mode == IIV_MODE_HGR ? 14 : 13;
+  const uint32_t n = 1u << bits, n_off = mode == IIV_MODE_HGR ? 2 : 4;
+  IIV_REQUIRE(row_begin <= row_end && row_end <= n, "bad row range [%u,%u)", row_begin, row_end);
+  IIV_REQUIRE(bands >= 1 && bands <= 4096, "bad band count %d", bands);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t pitch = (size_t)n * 2;
+  if (row_begin == row_end) return 0;
+  if (layout == IIV_LAYOUT_SYMMETRIC) bands = 1;
+  const uint32_t rows = row_end - row_begin;
+  const uint32_t per = (rows + (uint32_t)bands - 1) / (uint32_t)bands;
+  for (uint32_t o = 0; o < n_off; ++o) {
+    for (uint32_t r0 = row_begin; r0 < row_end; r0 += per) {
+      const uint32_t r1 = r0 + per < row_end ? r0 + per : row_end;
+      // columns j < r1 - 1 cover every j < i of the band; rounded up to 64 bytes
+      size_t width = layout == IIV_LAYOUT_SYMMETRIC ? pitch : (((size_t)(r1 - 1) * 2 + 63) & ~(size_t)63);
+      if (width > pitch) width = pitch;
+      if (width == 0) continue;
+      const size_t at = ((size_t)o << (2 * bits)) + ((size_t)r0 << bits);
+      IIV_CUDA(cudaMemcpy2DAsync(h_table + at, pitch, d_table + at, pitch, width, r1 - r0,
+                                 cudaMemcpyDeviceToHost, st));
+    }
+  }
+  return 0;
+}
+
 extern "C" int iiv_table_symmetrise(int mode, uint16_t* d_table, void* stream) {
   IIV_REQUIRE(d_table, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;

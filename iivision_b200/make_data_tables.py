@@ -141,34 +141,56 @@ def compute_edit_distance(edp: EditDistanceParams, bitmap_cls: Type[screen.Bitma
     Returns the reference's array: uint16[(len(BYTE_MASKS), 4**MASKED_BITS)],
     entry (i << bits) + j filled for j < i only (make_data_tables.py:156-172).
     ``nominal_colours`` only validated pixel values upstream and is ignored.
+
+    The array is READ-ONLY (``np.array(result)`` gives a private writable copy): it is a
+    view of recycled page-locked memory whose upper triangle is known to be zero, which is
+    what lets the device-to-host copy skip it.  The reference's callers only read the
+    result (make_data_tables.py:186-188 saves it).
     """
+    m = _mode_of(bitmap_cls)
     table = compute_edit_distance_device(edp, bitmap_cls, ops.LAYOUT_TRIANGULAR)
-    host = _pinned_result(tuple(table.shape))
-    host.copy_(table, non_blocking=True)
+    host, arr = _pinned_pool.lease(tuple(table.shape))
+    ops.table_download(m, table, host.data_ptr(), layout=ops.LAYOUT_TRIANGULAR)
     torch.cuda.current_stream().synchronize()
-    return host.numpy()      # the array keeps `host` alive; see _pinned_result
+    return arr
 
 
-_pinned_pool = []
+class _PinnedPool:
+    """Page-locked uint16 buffers for tables on their way to the host.  cudaHostAlloc of
+    1 GiB costs tens of milliseconds, more than the copy itself, so buffers are recycled: a
+    lease hands out a read-only array over a buffer and the buffer returns to the pool when
+    that array -- and with it every view derived from it, which numpy chains to it through
+    ``.base`` -- has been garbage collected.  Buffers start zeroed and are only ever written
+    below the diagonal, so a recycled buffer is still zero everywhere else."""
+
+    def __init__(self, keep: int = 4):
+        self.keep = keep
+        self.free = []
+
+    def lease(self, shape):
+        import weakref
+        host = None
+        for k, t in enumerate(self.free):
+            if tuple(t.shape) == shape:
+                host = self.free.pop(k)
+                break
+        if host is None:
+            host = self._alloc(shape)
+        arr = host.numpy()
+        arr.flags.writeable = False
+        weakref.finalize(arr, self._release, host)
+        return host, arr
+
+    @staticmethod
+    def _alloc(shape):
+        return torch.zeros(shape, dtype=torch.uint16, pin_memory=True)
+
+    def _release(self, host):
+        if len(self.free) < self.keep:
+            self.free.append(host)
 
 
-def _pinned_result(shape) -> torch.Tensor:
-    """Page-locked uint16 buffer for a table on its way to the host.  cudaHostAlloc of
-    1 GiB costs tens of milliseconds, more than the copy itself, so buffers are kept and
-    handed out again once the array returned to the caller has been dropped: a live numpy
-    view (or anything derived from it) holds a reference to the tensor's storage."""
-    try:
-        use_count = torch._C._storage_Use_Count
-    except AttributeError:       # no way to tell whether a buffer is still in use
-        return torch.empty(shape, dtype=torch.uint16, pin_memory=True)
-    for t in _pinned_pool:
-        # 2 = the pooled tensor itself + the temporary storage object made for the query
-        if tuple(t.shape) == shape and use_count(t.untyped_storage()._cdata) <= 2:
-            return t
-    t = torch.empty(shape, dtype=torch.uint16, pin_memory=True)
-    if len(_pinned_pool) < 4:
-        _pinned_pool.append(t)
-    return t
+_pinned_pool = _PinnedPool()
 
 
 def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,

@@ -122,6 +122,12 @@ def table_generate(mode, lut, layout=LAYOUT_SYMMETRIC, row_begin=0, row_end=None
     return out
 
 
+def fill_probe(buf: torch.Tensor, variant: int = 0) -> None:
+    """Write-only stream over ``buf`` (0 = cudaMemsetAsync, 1 = one 16-byte store per
+    thread): the ceiling bench.py quotes next to the generator."""
+    check(lib.iiv_fill_probe(_ptr(buf), buf.numel() * buf.element_size(), variant, _stream()))
+
+
 def launches_per_table_generate() -> int:
     """Kernels one iiv_table_generate call launches (pixel prologue + generator)."""
     return 2
@@ -148,6 +154,24 @@ def table_generate_scatter(mode, lut, peer_ptrs, rank, row_begin, row_end,
     check(lib.iiv_table_generate_scatter(
         m, lut.ctypes.data, ctypes.cast(arr, ctypes.c_void_p), n, rank,
         int(multicast_ptr) or None, row_begin, row_end, layout, _stream()))
+
+
+DOWNLOAD_BANDS = 32
+
+
+def table_download(mode, table: torch.Tensor, host_ptr: int, row_begin=0, row_end=None,
+                   layout=LAYOUT_TRIANGULAR, bands: int = DOWNLOAD_BANDS) -> None:
+    """The device-to-host leg of compute_edit_distance: rows [row_begin, row_end) of every
+    offset into the host table at ``host_ptr`` (full-table base address, page-locked).  In
+    the triangular layout only j < i moves; the rest of the host buffer must already be
+    zero.  Stream-ordered; the caller synchronises."""
+    m = mode_id(mode)
+    if row_end is None:
+        row_end = 1 << MASKED_BITS[m]
+    if tuple(table.shape) != table_shape(m) or table.dtype != torch.uint16:
+        raise ValueError("table must be uint16 %r" % (table_shape(m),))
+    check(lib.iiv_table_download(m, _ptr(table), int(host_ptr), row_begin, row_end, layout,
+                                 bands, _stream()))
 
 
 def table_symmetrise(mode, table: torch.Tensor) -> torch.Tensor:

@@ -52,6 +52,17 @@ extern "C" {
 const char* iiv_last_error(void);
 int iiv_version(void);
 
+/* Device-wide hint (cudaLimitMaxL2FetchGranularity): how much L2 fetches from HBM per miss,
+ * 32, 64 or 128 bytes.  The scorer's table reads (screen.py:441, :486) are 2-byte gathers
+ * spread over the whole table; 32 keeps a miss at one sector. */
+int iiv_set_l2_fetch_granularity(size_t bytes);
+size_t iiv_get_l2_fetch_granularity(void);
+
+/* Measurement aid (no reference counterpart): overwrite `bytes` of d_buf with a write-only
+ * stream, variant 0 = cudaMemsetAsync, 1 = a kernel doing one 16-byte store per thread.
+ * bench.py times it next to the table generator as the write-only HBM ceiling. */
+int iiv_fill_probe(void* d_buf, size_t bytes, int variant, void* stream);
+
 /* Class constants: MASKED_BITS, MASKED_DOTS, len(BYTE_MASKS), PHASES
  * (screen.py:617-645 HGR, :887-919 DHGR). phases4 receives n_offsets values. */
 int iiv_mode_info(int mode, int* masked_bits, int* masked_dots, int* n_offsets,
@@ -100,6 +111,16 @@ int iiv_table_generate_scatter(int mode, const int32_t* h_lut,
                                int rank, uint16_t* d_multicast_table,
                                uint32_t row_begin, uint32_t row_end, int layout,
                                void* stream);
+
+/* The device-to-host leg of compute_edit_distance (make_data_tables.py:111-174 returns a host
+ * array): rows [row_begin, row_end) of every offset of d_table go to the same place in
+ * h_table (both are FULL-table base pointers).  IIV_LAYOUT_TRIANGULAR moves only the columns
+ * that can be nonzero (j < i), in `bands` row bands of one 2-D copy each, and does not touch
+ * the rest of h_table: the caller passes a buffer whose other bytes are already zero.
+ * Asynchronous on `stream` when h_table is page-locked. */
+int iiv_table_download(int mode, const uint16_t* d_table, uint16_t* h_table,
+                       uint32_t row_begin, uint32_t row_end, int layout, int bands,
+                       void* stream);
 
 /* Bitmap.edit_distances' in-memory transform (screen.py:358-365):
  * new[y] = old[y] + old[transpose(y)], in place, all offsets. */

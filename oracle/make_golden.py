@@ -59,6 +59,12 @@ STREAM_CASES = [
     ("dhgr_sparse", "DHGR", 4, 0.05, 2, 7, 980, 292),
     ("hgr_full", "HGR", 3, 1.0, 3, 0, 980, 292),
     ("hgr_sparse", "HGR", 4, 0.02, 4, 11, 600, 292),
+    # one generator pulled far more than 2048 times (HGR never flips banks, so
+    # --every_n_video_frames 5 at 30 fps is 2450 pulls, main.py:29, movie.py:81-95); the
+    # second and third exhaust the first-pass heap and go on popping re-queued cells
+    ("hgr_long_generator", "HGR", 3, 1.0, 6, 2, 2450, 292),
+    ("hgr_exhaust", "HGR", 2, 1.0, 7, 3, 7000, 292),
+    ("dhgr_long_generator", "DHGR", 2, 1.0, 8, 4, 5000, 10 ** 9),
 ]
 
 
@@ -441,6 +447,15 @@ def main():
         print("long streams"); gen_long_hashes()
         return
     ns = ref_harness.load()
+    if "--streams" in sys.argv:       # --streams name[,name...]: just those stream fixtures
+        wanted = sys.argv[sys.argv.index("--streams") + 1].split(",")
+        for mode in ("HGR", "DHGR"):
+            cases = [c for c in STREAM_CASES if c[1] == mode and c[0] in wanted]
+            if cases:
+                table = symmetric_table(mode)
+                for case in cases:
+                    gen_stream(ns, case, table)
+        return
     print("helpers"); gen_helpers(ns)
     print("byte stream"); gen_byte_stream(ns)
     if "--helpers-only" in sys.argv:

@@ -282,17 +282,26 @@ def test_compute_edit_distance_results_do_not_alias(mods, oracle_luts):
     """The pinned staging buffers are recycled only after the caller dropped the array."""
     edp = mods.mdt.compute_substitute_costs(mods.palette.NTSCPalette)
     a = mods.mdt.compute_edit_distance(edp, mods.screen.DHGRBitmap)
-    keep = a[0, 5000:5010].copy()
+    at = 5000 * 8192 + 100                        # row 5000, columns 100..109 (j < i)
+    keep = a[0, at:at + 10].copy()
+    assert keep.any()
     view = a[1]                                   # a derived view keeps the buffer busy
     edp2 = mods.mdt.compute_substitute_costs(mods.palette.IIGSPalette)
     b = mods.mdt.compute_edit_distance(edp2, mods.screen.DHGRBitmap)
     assert not np.shares_memory(a, b)
-    assert np.array_equal(a[0, 5000:5010], keep) and not np.array_equal(a, b)
+    assert not a.flags.writeable and not b.flags.writeable     # documented: read-only result
+    assert np.array_equal(a[0, at:at + 10], keep) and not np.array_equal(a, b)
     ptr = a.ctypes.data
     del a, view
+    # EditDistanceParams keeps its arrays as CLASS attributes, like the reference
+    # (make_data_tables.py:30-52): edp now carries the IIGS costs edp2 was filled with
     c = mods.mdt.compute_edit_distance(edp, mods.screen.DHGRBitmap)
     assert c.ctypes.data == ptr                   # recycled now
-    assert np.array_equal(c[0, 5000:5010], keep)
+    assert np.array_equal(c, b)
+    # a recycled buffer is still zero above the diagonal (only j < i is ever copied into it)
+    from oracle import tables
+    want, _ = tables.build_table("DHGR", oracle_luts[0], triangular=True)
+    assert np.array_equal(c, want)
 
 
 @pytest.mark.parametrize("mode", ["HGR", "DHGR"])

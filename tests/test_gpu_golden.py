@@ -95,7 +95,8 @@ def test_scorer_primitives(ops, device_tables, mode):
         assert np.array_equal(a.cpu().numpy(), g["apply_aux"])
 
 
-@pytest.mark.parametrize("name", ["dhgr_full", "dhgr_sparse", "hgr_full", "hgr_sparse"])
+@pytest.mark.parametrize("name", ["dhgr_full", "dhgr_sparse", "hgr_full", "hgr_sparse",
+                                  "hgr_long_generator", "hgr_exhaust", "dhgr_long_generator"])
 def test_opcode_streams(ops, device_tables, name):
     import torch
     g = np.load(os.path.join(GOLDEN, "stream_%s.npz" % name))

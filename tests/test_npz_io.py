@@ -98,3 +98,38 @@ def test_reserved_member_name(tmp_path):
     npz_io = _load_module()
     with pytest.raises(ValueError):
         npz_io.savez_compressed(str(tmp_path / "x.npz"), **{npz_io.PIECES: np.zeros(1)})
+
+
+def test_pinned_pool_recycles_only_dead_leases(monkeypatch):
+    """make_data_tables._PinnedPool: a buffer returns to the pool when the leased array AND
+    every view derived from it are gone (numpy chains views to the leased array)."""
+    import gc
+    torch = pytest.importorskip("torch")
+    try:
+        from iivision_b200 import make_data_tables as mdt
+    except ImportError as e:       # library not built
+        pytest.skip(str(e))
+    pool = mdt._PinnedPool(keep=2)
+    made = []
+
+    def alloc(shape):
+        made.append(1)
+        return torch.zeros(shape, dtype=torch.uint16)
+    monkeypatch.setattr(pool, "_alloc", alloc)
+    host, a = pool.lease((2, 64))
+    del host
+    assert not a.flags.writeable and a.shape == (2, 64)
+    with pytest.raises(ValueError):
+        a[0, 0] = 1
+    view = a[1, 3:9]
+    ptr = a.ctypes.data
+    del a
+    gc.collect()
+    _, b = pool.lease((2, 64))
+    assert len(made) == 2 and b.ctypes.data != ptr        # the view still pins the first
+    del view
+    gc.collect()
+    _, c = pool.lease((2, 64))
+    assert len(made) == 2 and c.ctypes.data == ptr        # now recycled
+    _, d = pool.lease((4, 8))
+    assert len(made) == 3                                 # other shapes get their own

@@ -11,7 +11,7 @@ import pytest
 from oracle import scorer
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-STREAMS = ["dhgr_full", "dhgr_sparse", "hgr_full", "hgr_sparse"]
+STREAMS = ["dhgr_full", "dhgr_sparse", "hgr_full", "hgr_sparse", "hgr_long_generator", "hgr_exhaust", "dhgr_long_generator"]
 
 
 def load(name):

@@ -21,6 +21,17 @@ def _oracle_generate(mode, lut, layout, begin, end, out):
     tables.build_table(name, lut, begin, end, triangular=(layout == 0), out=view)
 
 
+def _host_download(mode, table, host_ptr, begin, end):
+    """Stand-in for ops.table_download on CPU tensors: the rows' lower-triangle columns."""
+    import ctypes
+    n = 1 << 13
+    src = table.view(torch.int16).numpy().view(np.uint16).reshape(4, n, n)
+    dst = np.ctypeslib.as_array(ctypes.cast(host_ptr, ctypes.POINTER(ctypes.c_uint16)),
+                                shape=(4, n, n))
+    width = max(end - 1, 0)
+    dst[:, begin:end, :width] = src[:, begin:end, :width]
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -36,6 +47,17 @@ def _worker(rank, world, port, q):
             want, _ = tables.build_table("DHGR", lut, triangular=(layout == 0))
             got = out.view(torch.int16).numpy().view(np.uint16)
             assert np.array_equal(got, want), "layout %d rank %d" % (layout, rank)
+        # host delivery: every rank copies its row block into one shared host array
+        host = parallel.SharedHostTable("DHGR", register=False)
+        try:
+            dev = torch.zeros((4, 1 << 26), dtype=torch.int16).view(torch.uint16)
+            got = parallel.compute_edit_distance_sharded(
+                "DHGR", lut, host, device_table=dev, generate_fn=_oracle_generate,
+                download_fn=_host_download)
+            want, _ = tables.build_table("DHGR", lut, triangular=True)
+            assert np.array_equal(got, want), "shared host table, rank %d" % rank
+        finally:
+            host.close()
         lo, hi = parallel.shard_range(5, world, rank)
         got = parallel.gather_clip_outputs(np.arange(lo, hi), 5)
         if rank == 0:
@@ -56,6 +78,13 @@ def test_partitions():
         assert len({e - b for b, e in parts}) == 1
     with pytest.raises(ValueError):
         parallel.row_partition(8192, 3)
+    for world in (1, 2, 4, 8):
+        blocks = [parallel.triangle_row_blocks(8192, world, r) for r in range(world)]
+        flat = sorted(b for bl in blocks for b in bl)
+        assert flat[0][0] == 0 and flat[-1][1] == 8192
+        assert all(a[1] == b[0] for a, b in zip(flat, flat[1:]))
+        below = [sum(sum(range(b, e)) for b, e in bl) for bl in blocks]   # entries j < i
+        assert max(below) - min(below) <= 8192 * (8192 // (2 * world))
     for n, world in ((64, 8), (5, 2), (3, 4), (0, 2)):
         spans = [parallel.shard_range(n, world, r) for r in range(world)]
         assert spans[0][0] == 0 and spans[-1][1] == n
