@@ -493,8 +493,9 @@ def facade_figures(torch, n_frames=8):
     """The reference-facing call for path 2: video.Video.encode_frame pulled the way
     Movie.encode pulls it (a new generator per frame and per bank flip, one next() per
     audio tick), host arrays in and out -- targets are built from host memory maps, the
-    encoder state and both global MT19937 generators are uploaded per generator and
-    written back at its commit, opcode tuples are read on the host."""
+    encoder state stays on the device (video.py syncs its host attributes on access), both
+    global MT19937 generators are kept in step at every generator's end, opcode tuples are
+    read on the host."""
     import contextlib
     import io
     import random
@@ -520,7 +521,8 @@ def facade_figures(torch, n_frames=8):
             if frame == 1 and t0 is None:      # frame 0 is the warm-up
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-            if frame != tgt_frame:             # one target bitmap per frame (movie.py:81-91)
+            new_target = frame != tgt_frame
+            if new_target:                     # one target bitmap per frame (movie.py:81-91)
                 tgt_frame = frame
                 tgt = screen.DHGRBitmap(
                     palette=palette.Palette.NTSC,
@@ -531,10 +533,14 @@ def facade_figures(torch, n_frames=8):
                 next(op_seq)
             if t0 is not None:
                 pulled += budget
-                # per generator: state up (packed, 2 maps, 2 priorities, 2 MT blobs) and
-                # target up; opcodes, segment info and state down
-                h2d += 32 * 128 * 8 + 2 * 8192 + 2 * 32768 + 2 * 2560 + 2 * 8192 + 32768
-                d2h += budget * 8 + 64 + 32 * 128 * 8 + 2 * 8192 + 2 * 32768 + 2 * 2560 + 64
+                # per generator: opcode records, segment info and the state's tail (both
+                # MT19937 states + flags) come down; per frame the target goes up once
+                # (two memory maps; the packed words are made on the device).  The encoder
+                # state itself stays on the device.
+                d2h += budget * 8 + 64 + 2 * 2560 + 64
+                if new_target:
+                    h2d += 2 * 8192
+                    d2h += 32768        # Bitmap.packed of the target, a host attribute
         op_seq.close()
         torch.cuda.synchronize()
     dt = time.perf_counter() - t0

@@ -75,6 +75,12 @@ PROTOTYPES = {
     "iiv_encode_clips_planned": (c_int, [c_int, c_int, c_void_p, c_size_t, c_void_p,
                                          c_void_p, c_int, c_void_p, c_void_p, c_int,
                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    "iiv_encode_generator": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
+    "iiv_event_create": (c_void_p, []),
+    "iiv_event_wait": (c_int, [c_void_p]),
+    "iiv_event_destroy": (c_int, [c_void_p]),
     "iiv_mt_draw": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "iiv_stream_length": (c_size_t, [c_size_t, c_int]),
     "iiv_stream_ticks_within": (c_size_t, [c_size_t, c_size_t]),

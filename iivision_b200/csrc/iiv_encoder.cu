@@ -316,6 +316,14 @@ __device__ __forceinline__ void apply_store(uint64_t* src, uint8_t* mem, int pag
   mem[page * 256 + offset] = (uint8_t)value;
 }
 
+// Optional extras of a launch (all zero for the plain batch call).
+struct EncodeExtras {
+  int3 inline_segment;      // the schedule of a one-segment launch (segments == nullptr)
+  const uint8_t* state_in;  // clip 0 starts from this blob instead of its own (one clip only)
+  uint8_t* tail_out;        // the final state's tail (generators + flags) is ALSO written here
+  uint8_t* opcodes_mirror;  // every segment's opcode records are ALSO written here (clip 0)
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
@@ -324,7 +332,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
               const int32_t* __restrict__ segments, int n_segments,
               const uint16_t* __restrict__ table, uint8_t* __restrict__ opcodes,
               int64_t total_budget, int64_t* __restrict__ seg_info,
-              uint64_t* __restrict__ overflow, int overflow_cap) {
+              uint64_t* __restrict__ overflow, int overflow_cap,
+              const __grid_constant__ EncodeExtras extras) {
   using M = Mode<MODE>;
   constexpr int kBanks = MODE == IIV_MODE_DHGR ? 2 : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -334,6 +343,14 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
   const int lane = t & 31, warp = t >> 5;
   const int clip = blockIdx.x;
   uint8_t* state = states + (size_t)clip * state_stride;
+  const int3 inline_segment = extras.inline_segment;
+  if (extras.state_in != nullptr && extras.state_in != state) {
+    // start from another blob: everything the kernel does not rewrite must carry over
+    const uint4* in = reinterpret_cast<const uint4*>(extras.state_in);
+    uint4* out = reinterpret_cast<uint4*>(state);
+    for (int k = threadIdx.x; k < (int)(kStateBytes / 16); k += kThreads) out[k] = in[k];
+    __syncthreads();
+  }
   uint64_t* g_packed = reinterpret_cast<uint64_t*>(state + kOffPacked);
   uint32_t* g_mt_np = reinterpret_cast<uint32_t*>(state + kOffMtNp);
   uint32_t* g_mt_py = reinterpret_cast<uint32_t*>(state + kOffMtPy);
@@ -372,9 +389,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
   const int pushed_cap = kPushedCap + (ovf != nullptr ? overflow_cap : 0);
 
   for (int seg = 0; seg < n_segments; ++seg) {
-    const int frame = segments[3 * seg + 0];
-    const int is_aux = segments[3 * seg + 1];
-    const int budget = segments[3 * seg + 2];
+    // (a single segment may ride in the kernel parameters: segments == nullptr)
+    const int frame = segments ? segments[3 * seg + 0] : inline_segment.x;
+    const int is_aux = segments ? segments[3 * seg + 1] : inline_segment.y;
+    const int budget = segments ? segments[3 * seg + 2] : inline_segment.z;
     int64_t* info = seg_info + ((size_t)clip * n_segments + seg) * 8;
     const long long clk_seg = clock64();
     if (budget <= 0) {  // generator created but never pulled: no side effects
@@ -1409,6 +1427,21 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       info[7] = (int64_t)sm.wmin64[1];             // decision-warp cycles waiting for MT / applier
       if (out_of_work) g_flags[is_aux ? 1 : 0] = 1;   // video.py:189
     }
+    if (extras.opcodes_mirror != nullptr) {
+      // second copy of the segment's records for a caller that reads them on the host (a
+      // page-locked buffer mapped into the device's address space): coalesced, all threads,
+      // off the opcode loop -- the decision warp itself only ever stores to device memory
+      __syncthreads();
+      __threadfence_block();
+      uint2* dst = reinterpret_cast<uint2*>(extras.opcodes_mirror) + (seg_out - opcodes) / 8;
+      const volatile uint2* srcp = reinterpret_cast<const volatile uint2*>(seg_out);
+      for (int k = t; k < budget; k += kThreads) {
+        uint2 v;
+        v.x = srcp[k].x;
+        v.y = srcp[k].y;
+        dst[k] = v;
+      }
+    }
     op_out += (size_t)budget * 8;
     __syncthreads();
     for (int k = t; k < kCells; k += kThreads) g_prio[k] = sm.prio[k];
@@ -1429,6 +1462,14 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     g_mt_np[624] = (uint32_t)pos_np;
     g_mt_py[624] = (uint32_t)pos_py;
     if (error_flags) atomicOr(&g_flags[2], error_flags);
+  }
+  if (extras.tail_out != nullptr) {
+    // the same tail once more, for a caller that wants it without a copy of its own (a
+    // page-locked host buffer mapped into the device's address space)
+    __syncthreads();
+    uint32_t* tail = reinterpret_cast<uint32_t*>(extras.tail_out);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(state + kOffMtNp);
+    for (int k = t; k < (int)((kStateBytes - kOffMtNp) / 4); k += kThreads) tail[k] = src[k];
   }
 }
 
@@ -1495,7 +1536,8 @@ static int launch_encode(int mode, int n_clips, uint8_t* d_state, size_t state_s
                          const uint8_t* d_target_mem, const uint64_t* d_target_packed,
                          int n_frames, const int32_t* d_segments, int n_segments, int64_t total,
                          int max_budget, const uint16_t* d_table, uint8_t* d_opcodes,
-                         int64_t* d_seg_info, cudaStream_t st) {
+                         int64_t* d_seg_info, cudaStream_t st,
+                         EncodeExtras extras = EncodeExtras{}) {
   const size_t smem = sizeof(Smem);
   cudaError_t e;
   // An opcode re-queues at most two cells (video.py:173-178): a segment of more than
@@ -1517,14 +1559,16 @@ static int launch_encode(int mode, int n_clips, uint8_t* d_state, size_t state_s
     if (e == cudaSuccess)
       encode_kernel<IIV_MODE_HGR><<<n_clips, kThreads, smem, st>>>(
           d_state, state_stride, d_target_mem, d_target_packed, n_frames, d_segments,
-          n_segments, d_table, d_opcodes, total, d_seg_info, d_overflow, overflow_cap);
+          n_segments, d_table, d_opcodes, total, d_seg_info, d_overflow, overflow_cap,
+          extras);
   } else {
     e = cudaFuncSetAttribute(encode_kernel<IIV_MODE_DHGR>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       encode_kernel<IIV_MODE_DHGR><<<n_clips, kThreads, smem, st>>>(
           d_state, state_stride, d_target_mem, d_target_packed, n_frames, d_segments,
-          n_segments, d_table, d_opcodes, total, d_seg_info, d_overflow, overflow_cap);
+          n_segments, d_table, d_opcodes, total, d_seg_info, d_overflow, overflow_cap,
+          extras);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (d_overflow) cudaFreeAsync(d_overflow, st);
@@ -1626,6 +1670,61 @@ extern "C" int iiv_encode_clips_planned(int mode, int n_clips, uint8_t* d_state,
   return launch_encode(mode, n_clips, d_state, state_stride, d_target_mem, d_target_packed,
                        n_frames, d_segments, n_segments, total, max_budget, d_table, d_opcodes,
                        d_seg_info, (cudaStream_t)stream);
+}
+
+// One encode_frame generator of the Python facade as ONE launch (the facade's per-generator
+// cost is host time and launch gaps: a dozen separate tensor operations and copies cost more
+// than the kernel's own fixed costs).  The kernel starts from d_state_in, leaves the state in
+// d_state_out, and writes its results straight into the caller's page-locked host buffers
+// through their device mappings: no copy is enqueued at all.
+extern "C" int iiv_encode_generator(int mode, const uint8_t* d_state_in, uint8_t* d_state_out,
+                                    const uint8_t* d_target_mem,
+                                    const uint64_t* d_target_packed, int is_aux, int budget,
+                                    const uint16_t* d_table, uint8_t* d_opcodes,
+                                    uint8_t* h_opcodes, int64_t* h_seg_info,
+                                    uint8_t* h_state_tail, void* event, void* stream) {
+  IIV_REQUIRE(d_opcodes && h_opcodes && h_seg_info && h_state_tail && d_state_in,
+              "null pointer");
+  IIV_REQUIRE(!(is_aux && mode == IIV_MODE_HGR), "HGR has no aux bank");
+  IIV_REQUIRE(budget >= 1 && budget <= kMaxBudget, "budget %d outside 1..%d", budget, kMaxBudget);
+  // device views of the host buffers (identical under unified addressing, but ask)
+  uint8_t* m_opcodes = nullptr;
+  int64_t* m_info = nullptr;
+  uint8_t* m_tail = nullptr;
+  IIV_CUDA(cudaHostGetDevicePointer((void**)&m_opcodes, h_opcodes, 0));
+  IIV_CUDA(cudaHostGetDevicePointer((void**)&m_info, h_seg_info, 0));
+  IIV_CUDA(cudaHostGetDevicePointer((void**)&m_tail, h_state_tail, 0));
+  int rc = check_encode_args(mode, 1, d_state_out, kStateBytes, d_target_mem, d_target_packed,
+                             1, 1, d_table, m_info);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  EncodeExtras extras = {};
+  extras.inline_segment = make_int3(0, is_aux ? 1 : 0, budget);
+  extras.state_in = d_state_in;
+  extras.tail_out = m_tail;
+  extras.opcodes_mirror = m_opcodes;
+  rc = launch_encode(mode, 1, d_state_out, kStateBytes, d_target_mem, d_target_packed, 1,
+                     nullptr, 1, budget, budget, d_table, d_opcodes, m_info, st, extras);
+  if (rc) return rc;
+  if (event) IIV_CUDA(cudaEventRecord((cudaEvent_t)event, st));
+  return 0;
+}
+
+extern "C" void* iiv_event_create(void) {
+  cudaEvent_t ev = nullptr;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  return ev;
+}
+
+extern "C" int iiv_event_wait(void* event) {
+  IIV_REQUIRE(event, "null event");
+  IIV_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+  return 0;
+}
+
+extern "C" int iiv_event_destroy(void* event) {
+  if (event) IIV_CUDA(cudaEventDestroy((cudaEvent_t)event));
+  return 0;
 }
 
 extern "C" int iiv_mt_draw(uint32_t* d_mt625, uint32_t* d_words, int n, void* stream) {

@@ -162,7 +162,7 @@ class Bitmap:
         self.aux_memory = aux_memory
         self.PACKED_BITS = self.HEADER_BITS + self.BODY_BITS + self.FOOTER_BITS
         self.SCREEN_BYTES = np.uint64(len(self.BYTE_MASKS))
-        self.packed = np.empty(shape=(32, 128), dtype=np.uint64)
+        self._packed = np.empty(shape=(32, 128), dtype=np.uint64)
         self._pack()
 
     # -- packing -----------------------------------------------------------------
@@ -211,11 +211,33 @@ class Bitmap:
 
     def _pack(self) -> None:
         """Pack MemoryMap into efficient representation for diffing
-        (screen.py:207-226 -> iiv_pack)."""
-        main = _h2d_u8(self.main_memory.page_offset)
-        aux = _h2d_u8(self.aux_memory.page_offset) if self.aux_memory is not None \
-            and self.MODE == ops.MODE_DHGR else None
-        self.packed = _d2h_u64(ops.pack(self.MODE, main, aux))
+        (screen.py:207-226 -> iiv_pack).  The packing runs on the device and nothing waits
+        for it: ``packed`` is fetched when it is first read.  The device copies of the
+        memory maps and of the packed words are kept, with the host values they were made
+        from, so that video.Video can score against this bitmap without uploading it."""
+        dhgr = self.aux_memory is not None and self.MODE == ops.MODE_DHGR
+        banks = [np.require(self.main_memory.page_offset, dtype=np.uint8, requirements=["C"])]
+        if dhgr:
+            banks.append(np.require(self.aux_memory.page_offset, dtype=np.uint8,
+                                    requirements=["C"]))
+        host = np.stack(banks)
+        tmem = torch.from_numpy(host).cuda()
+        dev = ops.pack(self.MODE, tmem[0], tmem[1] if dhgr else None)
+        self._packed = None
+        self._device_copy = (host, None, tmem, dev)
+
+    @property
+    def packed(self) -> np.ndarray:
+        """uint64[32][128] (screen.py:186-188), brought from the device on first use."""
+        if self._packed is None:
+            host, _, tmem, dev = self._device_copy
+            self._packed = _d2h_u64(dev)
+            self._device_copy = (host, self._packed.copy(), tmem, dev)
+        return self._packed
+
+    @packed.setter
+    def packed(self, value) -> None:
+        self._packed = value
 
     @classmethod
     def masked_update(cls, byte_offset: int, old_value: IntOrArray,

@@ -279,6 +279,25 @@ int iiv_encode_clips_planned(int mode, int n_clips, uint8_t* d_state,
                              int n_segments, const uint16_t* d_table, uint8_t* d_opcodes,
                              int64_t* d_seg_info, void* stream);
 
+/* One encode_frame generator (video.py:72-93) of ONE clip as a single kernel launch, for
+ * callers that pull opcodes on the host (the Python facade): the kernel starts from the
+ * state blob d_state_in, leaves the state in d_state_out (they may be the same blob), runs
+ * `budget` opcodes of (target, is_aux) and writes the opcode records (budget x 8 bytes), the
+ * segment info (8 x int64) and the tail of the state blob from field [5] on (both MT19937
+ * states and the flags) directly into the PAGE-LOCKED host buffers h_* through their device
+ * mappings -- no copies are enqueued (d_opcodes, budget x 8 bytes of device scratch, is where
+ * the opcode loop itself writes); `event` (from iiv_event_create, may be NULL) is recorded
+ * behind the kernel.  Nothing synchronises: iiv_event_wait does.
+ * d_target_mem / d_target_packed describe one frame. */
+int iiv_encode_generator(int mode, const uint8_t* d_state_in, uint8_t* d_state_out,
+                         const uint8_t* d_target_mem, const uint64_t* d_target_packed,
+                         int is_aux, int budget, const uint16_t* d_table,
+                         uint8_t* d_opcodes, uint8_t* h_opcodes, int64_t* h_seg_info,
+                         uint8_t* h_state_tail, void* event, void* stream);
+void* iiv_event_create(void);
+int iiv_event_wait(void* event);
+int iiv_event_destroy(void* event);
+
 /* ---- next row N2: player byte stream (movie.py, opcodes.py) --------------------- */
 
 /* Movie.emit_stream (movie.py:122-161) with Machine.emit (machine.py:11-25) and the

@@ -117,7 +117,7 @@ def test_bad_schedule_rejected(ops, device_tables):
     states = ops.new_clip_states(1)
     tmem = torch.zeros((1, 1, 1, 32, 256), dtype=torch.uint8, device="cuda")
     tp = torch.zeros((1, 1, 32, 128), dtype=torch.int64, device="cuda")
-    for segs in ([(1, 0, 5)], [(0, 1, 5)], [(0, 0, 100000)]):
+    for segs in ([(1, 0, 5)], [(0, 1, 5)], [(0, 0, (1 << 17) + 1)]):
         with pytest.raises(IIVError):
             ops.encode_clips("HGR", states, tmem, tp, segs, device_tables("HGR"))
 

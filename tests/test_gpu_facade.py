@@ -224,9 +224,11 @@ def test_video_budget_prediction(mods, oracle_tables, monkeypatch):
     ov = scorer.OracleVideo("DHGR", oracle_tables("DHGR"), py_rng=random.Random(5),
                             np_rng=np.random.RandomState(5))
     runs = []
-    real_run = mods.video._Run._run
-    monkeypatch.setattr(mods.video._Run, "_run",
-                        lambda self, budget: (runs.append(budget), real_run(self, budget))[1])
+    real_launch = mods.video.Video._launch
+    monkeypatch.setattr(
+        mods.video.Video, "_launch",
+        lambda self, base, tgt, is_aux, budget: (
+            runs.append(budget), real_launch(self, base, tgt, is_aux, budget))[1])
     tgt = otgt = None
     tgt_frame = -1
     first_frame_runs = None
@@ -246,11 +248,82 @@ def test_video_budget_prediction(mods, oracle_tables, monkeypatch):
                 a, b = next(seq), next(oseq)
                 assert (a[0], a[1], a[2]) == (int(b[0]), int(b[1]), [int(x) for x in b[2]])
             seq.close()
+    # (with the pipeline on, a generator's launch is issued while its predecessor is still
+    # being pulled; the order and the budgets of the launches are the schedule's all the same)
     later = [s_ for s_ in segs if s_[0] >= 1]
     assert runs[first_frame_runs:] == [s_[2] for s_ in later]
     assert np.array_equal(v.update_priority, ov.update_priority)
     assert np.array_equal(v.aux_update_priority, ov.aux_update_priority)
     assert np.array_equal(v.pixelmap.packed, ov.pixelmap.packed)
+
+
+@pytest.mark.parametrize("name", ["hgr_long_generator", "hgr_exhaust"])
+def test_video_facade_long_generators(mods, name):
+    """One generator pulled 2450 / 7000 times (HGR never flips banks; the reference's loop
+    is unbounded, video.py:121), against the reference's own stream."""
+    g = np.load(os.path.join(GOLDEN, "stream_%s.npz" % name))
+    seed = int(g["rng_seed"])
+    random.seed(seed)
+    np.random.seed(seed)
+    v = mods.video.Video(_Grabber(), ticks_per_second=14700., mode=mods.video_mode.VideoMode.HGR,
+                         palette=mods.palette.Palette.NTSC)
+    got = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for frame, is_aux, budget in g["segments"]:
+            tgt = mods.screen.HGRBitmap(palette=mods.palette.Palette.NTSC,
+                                        main_memory=mods.screen.MemoryMap(1, g["frames"][frame, 0].copy()))
+            op_seq = v.encode_frame(tgt, is_aux=False)
+            for _ in range(budget):
+                page, content, offs = next(op_seq)
+                got.append([page, content] + list(offs))
+    assert np.array_equal(np.array(got, np.uint8), g["opcodes"])
+    assert np.array_equal(v.pixelmap.packed, g["packed"])
+    assert np.array_equal(v.update_priority, g["priority_main"])
+    assert [random.getrandbits(32) for _ in range(4)] == g["next_python_words"].tolist()
+    assert np.random.randint(0, 256, size=4).tolist() == g["next_numpy_bytes"].tolist()
+
+
+def test_video_sees_foreign_draws_and_host_edits_between_generators(mods, oracle_tables):
+    """Between two generators other code may draw from the global generators and edit the
+    encoder's arrays (they are plain attributes upstream): the next generator starts from
+    exactly that, as the reference's would."""
+    from iivision_b200 import synth
+    from oracle import scorer
+    frames = synth.synthetic_frames("DHGR", 2, 0.6, seed=41)
+    segs = synth.movie_schedule("DHGR", 2)
+    random.seed(11)
+    np.random.seed(11)
+    v = mods.video.Video(_Grabber(), 14700., mode=mods.video_mode.VideoMode.DHGR)
+    opy, onp = random.Random(11), np.random.RandomState(11)
+    ov = scorer.OracleVideo("DHGR", oracle_tables("DHGR"), py_rng=opy, np_rng=onp)
+    tgt = otgt = None
+    with contextlib.redirect_stdout(io.StringIO()):
+        for n, (frame, is_aux, budget) in enumerate(segs):
+            if tgt is None or frame != segs[n - 1][0]:
+                tgt = mods.screen.DHGRBitmap(
+                    palette=mods.palette.Palette.NTSC,
+                    main_memory=mods.screen.MemoryMap(1, frames[frame, 0].copy()),
+                    aux_memory=mods.screen.MemoryMap(1, frames[frame, 1].copy()))
+                otgt = ov.target_bitmap(frames[frame, 0], frames[frame, 1])
+            if n == 2:        # somebody else uses the global generators
+                assert random.getrandbits(8) == opy.getrandbits(8)
+                assert np.random.randint(0, 256, size=3).tolist() == onp.randint(0, 256, size=3).tolist()
+            if n == 3:        # python stream only
+                random.random(), opy.random()
+            if n == 4:        # and the priorities are edited in place
+                v.update_priority[3, 10:20] += 7
+                ov.update_priority[3, 10:20] += 7
+                v.aux_update_priority[5, 0:8] = 0
+                ov.aux_update_priority[5, 0:8] = 0
+            seq, oseq = v.encode_frame(tgt, bool(is_aux)), ov.encode_frame(otgt, bool(is_aux))
+            for _ in range(budget):
+                a, b = next(seq), next(oseq)
+                assert (a[0], a[1], a[2]) == (int(b[0]), int(b[1]), [int(x) for x in b[2]]), n
+            seq.close()      # "between generators": Movie.encode drops the old one first
+    assert np.array_equal(v.update_priority, ov.update_priority)
+    assert np.array_equal(v.aux_update_priority, ov.aux_update_priority)
+    assert np.array_equal(v.pixelmap.packed, ov.pixelmap.packed)
+    assert random.getrandbits(32) == opy.getrandbits(32)
 
 
 def test_static_helpers_against_reference_fixture(mods):
