@@ -13,6 +13,7 @@ host cores (npz_io.py).
 
 import functools
 import os
+import zlib
 from typing import Iterable, Type
 
 import numpy as np
@@ -193,15 +194,42 @@ class _PinnedPool:
 _pinned_pool = _PinnedPool()
 
 
+DEFLATE_GROUP = 64      # device blocks (32 KiB each) per piece of load_member's index
+
+
 def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,
                        bitmap_cls: Type[screen.Bitmap],
                        nominal_colours: Type[colours.NominalColours] = None):
-    """Write file containing (D)HGR edit distance matrix for a palette."""
-    dist = compute_edit_distance(edp, bitmap_cls, nominal_colours)
+    """Write file containing (D)HGR edit distance matrix for a palette.
+
+    Same container and member as the reference's ``np.savez_compressed(data,
+    edit_distance=dist)`` (make_data_tables.py:186-188) -- ``np.load(...)['edit_distance']``
+    reads it -- but the table never comes to the host uncompressed: the device deflates it
+    where it was generated (ops.deflate_table) and only the compressed stream crosses PCIe."""
+    from . import deflate
+    m = _mode_of(bitmap_cls)
+    table = compute_edit_distance_device(edp, bitmap_cls, ops.LAYOUT_TRIANGULAR)
+    stream, sizes, block_crc, block_bytes = ops.deflate_table(m, table)
+    host = torch.empty(stream.shape, dtype=torch.uint8, pin_memory=True)
+    host.copy_(stream, non_blocking=True)
+    # while the stream comes home: checksums and the piece index
+    shape = tuple(table.shape)
+    like = np.broadcast_to(np.uint16(0), shape)
+    header = npz_io._npy_header(like)
+    body_crc = deflate.crc32_of_equal_parts(block_crc, block_bytes)
+    crc = deflate.crc32_combine(zlib.crc32(header), body_crc, len(block_crc) * block_bytes)
+    group = DEFLATE_GROUP if len(sizes) % DEFLATE_GROUP == 0 else 1
+    ends = np.cumsum(sizes.astype(np.int64))
+    comp_len = ends[group - 1::group] - np.concatenate(([0], ends[group - 1::group][:-1]))
+    comp_off = ends[group - 1::group] - comp_len
+    raw_len = group * block_bytes
+    group_crc = deflate.crc32_of_groups(block_crc, block_bytes, group)
+    pieces = [(k * raw_len, raw_len, int(comp_off[k]), int(comp_len[k]), int(group_crc[k]))
+              for k in range(len(comp_len))]
+    torch.cuda.current_stream().synchronize()
     data = "%s/%s_palette_%d_edit_distance.npz" % (
         DATA_DIR, bitmap_cls.NAME, pal.ID.value)
-    # same container and member as np.savez_compressed, deflated on all host cores
-    npz_io.savez_compressed(data, edit_distance=dist)
+    npz_io.savez_predeflated(data, "edit_distance", like, host.numpy(), crc, pieces)
 
 
 def main():

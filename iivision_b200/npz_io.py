@@ -88,6 +88,63 @@ def _member(f, pool, name: str, a: np.ndarray, level: int):
 PIECES = "__deflate_pieces__"
 
 
+def savez_predeflated(path, name: str, array_like, stream, raw_crc: int, pieces,
+                      level: int = 6) -> None:
+    """An ``.npz`` with ONE member whose body has already been deflated elsewhere (on the
+    device: ops.deflate_table).
+
+    ``array_like`` only describes the array (shape, dtype, C order: anything
+    ``header_data_from_array_1_0`` accepts, e.g. an ``np.broadcast_to`` view); ``stream`` is
+    the body's raw-deflate bytes as a sequence of byte-aligned, self-contained non-final
+    blocks; ``raw_crc`` the CRC-32 of the .npy header + body, i.e. of the member;
+    ``pieces`` rows of (raw offset in the body, raw length, offset in ``stream``, compressed
+    length, CRC-32 of those raw bytes) for ``load_member``'s parallel inflate."""
+    path = os.fspath(path)
+    if not path.endswith(".npz"):
+        path += ".npz"
+    header = _npy_header(array_like)
+    head = _deflate_piece((memoryview(header), level, False))
+    tail = b"\x01\x00\x00\xff\xff"            # final, empty stored block
+    stream = memoryview(stream)
+    body_raw = int(np.prod(array_like.shape)) * array_like.dtype.itemsize
+    raw_size = len(header) + body_raw
+    comp_size = len(head) + len(stream) + len(tail)
+    fname = (name + ".npy").encode("utf-8")
+    table = [(0, 0, len(header), 0, len(head), zlib.crc32(header))]
+    with open(path, "wb") as f:
+        extra = struct.pack("<HHQQ", 1, 16, raw_size, comp_size)
+        f.write(_LOCAL + struct.pack("<HHHHHIIIHH", 45, 0, 8, 0, _DOS_DATE, raw_crc,
+                                     0xffffffff, 0xffffffff, len(fname), len(extra))
+                + fname + extra)
+        data_start = f.tell()
+        f.write(head)
+        body_start = f.tell()
+        f.write(stream)
+        f.write(tail)
+        for raw_off, raw_len, comp_off, comp_len, crc in pieces:
+            table.append((0, len(header) + int(raw_off), int(raw_len),
+                          body_start + int(comp_off), int(comp_len), int(crc)))
+        # the header piece's file offset was not known when its row was made
+        table[0] = (0, 0, len(header), data_start, len(head), zlib.crc32(header))
+        records = [(fname, raw_crc, raw_size, comp_size, 0)]
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            rec, _ = _member(f, pool, PIECES, np.array(table, dtype=np.int64).reshape(-1, 6),
+                             level)
+        records.append(rec)
+        cd_start = f.tell()
+        for fn, crc, rs, cs, offset in records:
+            extra = struct.pack("<HHQQQ", 1, 24, rs, cs, offset)
+            f.write(_CENTRAL + struct.pack(
+                "<HHHHHHIIIHHHHHII", 45, 45, 0, 8, 0, _DOS_DATE, crc, 0xffffffff, 0xffffffff,
+                len(fn), len(extra), 0, 0, 0, 0, 0xffffffff) + fn + extra)
+        cd_size = f.tell() - cd_start
+        n = len(records)
+        f.write(_END64 + struct.pack("<QHHIIQQQQ", 44, 45, 45, 0, 0, n, n, cd_size, cd_start))
+        f.write(_END64_LOC + struct.pack("<IQI", 0, cd_start + cd_size, 1))
+        f.write(_END + struct.pack("<HHHHIIH", 0, 0, min(n, 0xffff), min(n, 0xffff),
+                                   0xffffffff, 0xffffffff, 0))
+
+
 def savez_compressed(path, level: int = 6, threads: int = None, index: bool = True,
                      **arrays) -> None:
     """Drop-in for ``np.savez_compressed(path, **arrays)`` (keyword form).  With
