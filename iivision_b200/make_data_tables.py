@@ -195,6 +195,39 @@ _pinned_pool = _PinnedPool()
 
 
 DEFLATE_GROUP = 64      # device blocks (32 KiB each) per piece of load_member's index
+STAGE_SLOTS, STAGE_BYTES = 3, 16 << 20
+_stage = {}
+
+
+def _staged_home(stream: torch.Tensor):
+    """Yields a device byte stream as host buffers, in order, through a small ring of
+    page-locked slots: while the caller consumes one slice (writes it to the file) the next
+    ones are already crossing PCIe.  A yielded buffer is valid until the next is asked for.
+    (Page-locking memory for the whole stream would cost more than the copy.)"""
+    dev = stream.device
+    if dev not in _stage:
+        _stage[dev] = [torch.empty(STAGE_BYTES, dtype=torch.uint8, pin_memory=True)
+                       for _ in range(STAGE_SLOTS)]
+    slots = _stage[dev]
+    total = stream.numel()
+    n = (total + STAGE_BYTES - 1) // STAGE_BYTES
+    events = [None] * n
+
+    def issue(k):
+        lo = k * STAGE_BYTES
+        hi = min(total, lo + STAGE_BYTES)
+        slots[k % STAGE_SLOTS][:hi - lo].copy_(stream[lo:hi], non_blocking=True)
+        events[k] = torch.cuda.Event()
+        events[k].record()
+
+    for k in range(min(n, STAGE_SLOTS)):
+        issue(k)
+    for k in range(n):
+        events[k].synchronize()
+        hi = min(total, (k + 1) * STAGE_BYTES)
+        yield slots[k % STAGE_SLOTS].numpy()[:hi - k * STAGE_BYTES]
+        if k + STAGE_SLOTS < n:
+            issue(k + STAGE_SLOTS)       # the consumer is done with slot k
 
 
 def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,
@@ -205,14 +238,15 @@ def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,
     Same container and member as the reference's ``np.savez_compressed(data,
     edit_distance=dist)`` (make_data_tables.py:186-188) -- ``np.load(...)['edit_distance']``
     reads it -- but the table never comes to the host uncompressed: the device deflates it
-    where it was generated (ops.deflate_table) and only the compressed stream crosses PCIe."""
+    where it was generated (ops.deflate_table) and only the compressed stream crosses PCIe,
+    slice by slice, while the slices before it are being written to the file."""
     from . import deflate
     m = _mode_of(bitmap_cls)
     table = compute_edit_distance_device(edp, bitmap_cls, ops.LAYOUT_TRIANGULAR)
     stream, sizes, block_crc, block_bytes = ops.deflate_table(m, table)
-    host = torch.empty(stream.shape, dtype=torch.uint8, pin_memory=True)
-    host.copy_(stream, non_blocking=True)
-    # while the stream comes home: checksums and the piece index
+    home = _staged_home(stream)
+    first = next(home)              # starts the copies; the bookkeeping below overlaps them
+    # checksums and the piece index
     shape = tuple(table.shape)
     like = np.broadcast_to(np.uint16(0), shape)
     header = npz_io._npy_header(like)
@@ -226,10 +260,11 @@ def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,
     group_crc = deflate.crc32_of_groups(block_crc, block_bytes, group)
     pieces = [(k * raw_len, raw_len, int(comp_off[k]), int(comp_len[k]), int(group_crc[k]))
               for k in range(len(comp_len))]
-    torch.cuda.current_stream().synchronize()
     data = "%s/%s_palette_%d_edit_distance.npz" % (
         DATA_DIR, bitmap_cls.NAME, pal.ID.value)
-    npz_io.savez_predeflated(data, "edit_distance", like, host.numpy(), crc, pieces)
+    import itertools
+    npz_io.savez_predeflated(data, "edit_distance", like, itertools.chain((first,), home),
+                             stream.numel(), crc, pieces)
 
 
 def main():

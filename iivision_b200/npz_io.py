@@ -88,29 +88,29 @@ def _member(f, pool, name: str, a: np.ndarray, level: int):
 PIECES = "__deflate_pieces__"
 
 
-def savez_predeflated(path, name: str, array_like, stream, raw_crc: int, pieces,
-                      level: int = 6) -> None:
+def savez_predeflated(path, name: str, array_like, stream, stream_len: int, raw_crc: int,
+                      pieces, level: int = 6) -> None:
     """An ``.npz`` with ONE member whose body has already been deflated elsewhere (on the
     device: ops.deflate_table).
 
     ``array_like`` only describes the array (shape, dtype, C order: anything
-    ``header_data_from_array_1_0`` accepts, e.g. an ``np.broadcast_to`` view); ``stream`` is
-    the body's raw-deflate bytes as a sequence of byte-aligned, self-contained non-final
-    blocks; ``raw_crc`` the CRC-32 of the .npy header + body, i.e. of the member;
-    ``pieces`` rows of (raw offset in the body, raw length, offset in ``stream``, compressed
-    length, CRC-32 of those raw bytes) for ``load_member``'s parallel inflate."""
+    ``header_data_from_array_1_0`` accepts, e.g. an ``np.broadcast_to`` view); ``stream``
+    yields the body's raw-deflate bytes in order, ``stream_len`` bytes in all, as buffers that
+    are only valid until the next one is asked for (a staging ring) -- a sequence of
+    byte-aligned, self-contained non-final blocks; ``raw_crc`` is the CRC-32 of the .npy
+    header + body, i.e. of the member; ``pieces`` rows of (raw offset in the body, raw
+    length, offset in the stream, compressed length, CRC-32 of those raw bytes) for
+    ``load_member``'s parallel inflate."""
     path = os.fspath(path)
     if not path.endswith(".npz"):
         path += ".npz"
     header = _npy_header(array_like)
     head = _deflate_piece((memoryview(header), level, False))
     tail = b"\x01\x00\x00\xff\xff"            # final, empty stored block
-    stream = memoryview(stream)
     body_raw = int(np.prod(array_like.shape)) * array_like.dtype.itemsize
     raw_size = len(header) + body_raw
-    comp_size = len(head) + len(stream) + len(tail)
+    comp_size = len(head) + int(stream_len) + len(tail)
     fname = (name + ".npy").encode("utf-8")
-    table = [(0, 0, len(header), 0, len(head), zlib.crc32(header))]
     with open(path, "wb") as f:
         extra = struct.pack("<HHQQ", 1, 16, raw_size, comp_size)
         f.write(_LOCAL + struct.pack("<HHHHHIIIHH", 45, 0, 8, 0, _DOS_DATE, raw_crc,
@@ -119,13 +119,22 @@ def savez_predeflated(path, name: str, array_like, stream, raw_crc: int, pieces,
         data_start = f.tell()
         f.write(head)
         body_start = f.tell()
-        f.write(stream)
+        written = 0
+        for part in stream:
+            part = memoryview(part)
+            f.write(part)
+            written += len(part)
+        if written != int(stream_len):
+            raise ValueError("stream of %d bytes, %d announced" % (written, stream_len))
         f.write(tail)
+        table = [(0, 0, len(header), data_start, len(head), zlib.crc32(header))]
         for raw_off, raw_len, comp_off, comp_len, crc in pieces:
             table.append((0, len(header) + int(raw_off), int(raw_len),
                           body_start + int(comp_off), int(comp_len), int(crc)))
-        # the header piece's file offset was not known when its row was made
-        table[0] = (0, 0, len(header), data_start, len(head), zlib.crc32(header))
+        if len(table) > 1:
+            # the final empty block rides with the last piece: the index covers the member
+            last = table[-1]
+            table[-1] = last[:4] + (last[4] + len(tail),) + last[5:]
         records = [(fname, raw_crc, raw_size, comp_size, 0)]
         with ThreadPoolExecutor(max_workers=1) as pool:
             rec, _ = _member(f, pool, PIECES, np.array(table, dtype=np.int64).reshape(-1, 6),

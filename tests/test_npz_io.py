@@ -133,3 +133,38 @@ def test_pinned_pool_recycles_only_dead_leases(monkeypatch):
     assert len(made) == 2 and c.ctypes.data == ptr        # now recycled
     _, d = pool.lease((4, 8))
     assert len(made) == 3                                 # other shapes get their own
+
+
+def test_predeflated_member_reads_like_numpys_and_by_pieces(tmp_path, monkeypatch):
+    """savez_predeflated: the body arrives already deflated (on the GPU path: from the
+    device) as byte-aligned non-final blocks, in slices; np.load reads the member and
+    load_member inflates it by the piece index without falling back to np.load."""
+    npz_io = _load_module()
+    rng = np.random.default_rng(5)
+    a = np.tril(rng.integers(0, 1800, size=(1024, 1024), dtype=np.uint16)).reshape(2, -1)
+    raw = a.tobytes()
+    part = 1 << 16
+    blocks, pieces, off = [], [], 0
+    for lo in range(0, len(raw), part):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        out = co.compress(raw[lo:lo + part]) + co.flush(zlib.Z_SYNC_FLUSH)
+        pieces.append((lo, part, off, len(out), zlib.crc32(raw[lo:lo + part])))
+        blocks.append(out)
+        off += len(out)
+    stream = b"".join(blocks)
+    slices = (stream[k:k + 100000] for k in range(0, len(stream), 100000))
+    like = np.broadcast_to(np.uint16(0), a.shape)
+    crc = zlib.crc32(npz_io._npy_header(like) + raw)
+    path = str(tmp_path / "pre.npz")
+    npz_io.savez_predeflated(path, "edit_distance", like, slices, len(stream), crc, pieces)
+    with np.load(path) as z:
+        assert np.array_equal(z["edit_distance"], a)
+    with zipfile.ZipFile(path) as z:
+        assert z.testzip() is None
+    def no_fallback(*args, **kw):
+        raise AssertionError("load_member fell back to np.load")
+    monkeypatch.setattr(npz_io.np, "load", no_fallback)
+    assert np.array_equal(npz_io.load_member(path, "edit_distance", threads=3), a)
+    with pytest.raises(ValueError):
+        npz_io.savez_predeflated(str(tmp_path / "short.npz"), "edit_distance", like,
+                                 [stream[:-1]], len(stream), crc, pieces)
