@@ -38,109 +38,103 @@ OpcodeCommand = enum.Enum("OpcodeCommand", _op_cmds())
 
 
 class Opcode:
-    """Base class for opcodes."""
+    """One operation of the player.  A subclass names its command, the attributes that make
+    up its payload (``FIELDS``, also the constructor's positional arguments) and how the
+    payload is laid out in the stream (``_payload``); equality, repr and emission follow
+    from those.  ``_START`` is the address of the player's implementation of the command."""
     COMMAND = None  # type: OpcodeCommand
+    FIELDS = ()     # type: Tuple[str, ...]
+    VECTORS = True  # whether the stream carries the address of this opcode before its data
+    _START = None   # type: int
 
-    # Offset of start byte of player opcode implementation
-    _START = None  # type: int
+    def __init__(self, *values):
+        if len(values) != len(self.FIELDS):
+            raise TypeError("%s takes %d argument(s)" % (type(self).__name__, len(self.FIELDS)))
+        for name, value in zip(self.FIELDS, values):
+            setattr(self, name, value)
 
     def __repr__(self):
         return "Opcode(%s)" % self.COMMAND.name
 
-    def __eq__(self, other):
-        if not isinstance(other, self.__class__):
-            return False
-        return self.__data_eq__(other)
-
     def __data_eq__(self, other):
-        raise NotImplementedError
+        return all(getattr(self, f) == getattr(other, f) for f in self.FIELDS)
+
+    def __eq__(self, other):
+        return isinstance(other, self.__class__) and self.__data_eq__(other)
+
+    __hash__ = None
 
     @staticmethod
     def emit_command(opcode: "Opcode") -> Iterator[int]:
+        """The two address bytes (high, low) that vector the player to ``opcode``."""
+        if not opcode.VECTORS:
+            return
         if not opcode._START:
             raise ValueError(
                 "Unable to find opcode address for %s in player debug symbols"
                 % opcode.COMMAND)
-        yield opcode._START >> 8
-        yield opcode._START & 0xff
+        yield from divmod(opcode._START, 256)
+
+    def _payload(self) -> Tuple[int, ...]:
+        return ()
 
     def emit_data(self) -> Iterator[int]:
-        return
+        yield from self._payload()
 
     def apply(self, state: Machine):
         pass
 
 
 class Header(Opcode):
-    """Video header opcode."""
+    """Video header: first bytes of the stream, not vectored to.  Padded with 0xff to the
+    size of a tick opcode so that ACKs fall at even intervals; last byte = video mode."""
     COMMAND = OpcodeCommand.HEADER
+    FIELDS = ("video_mode",)
+    VECTORS = False
 
     def __init__(self, mode: video_mode.VideoMode):
-        self.video_mode = mode
+        super().__init__(mode)
 
-    def __data_eq__(self, other):
-        return self.video_mode == other.video_mode
-
-    @staticmethod
-    def emit_command(opcode: "Opcode") -> Iterator[int]:
-        # does not explicitly vector to the next opcode
-        return
-
-    def emit_data(self) -> Iterator[int]:
-        # padded to the size of a tick opcode so that ACKs schedule evenly
-        for _ in range(6):
-            yield 0xff
-        yield self.video_mode.value
+    def _payload(self):
+        return (0xff,) * 6 + (self.video_mode.value,)
 
 
 class Nop(Opcode):
-    """NOP pad opcode that does nothing except vector to the next one."""
+    """Does nothing except vector to the next opcode."""
     COMMAND = OpcodeCommand.NOP
-
-    def __data_eq__(self, other):
-        return True
 
 
 class Terminate(Opcode):
-    """Terminates video playback."""
+    """Ends playback."""
     COMMAND = OpcodeCommand.TERMINATE
-
-    def __data_eq__(self, other):
-        return True
 
 
 class Ack(Opcode):
-    """Instructs player to perform TCP stream + buffer management."""
+    """Player does its TCP stream + buffer management; carries the low byte of the
+    $C054 / $C055 soft switch that steers the following stores to MAIN / AUX memory, and a
+    pad byte that completes the TCP frame."""
     COMMAND = OpcodeCommand.ACK
+    FIELDS = ("aux_active",)
 
     def __init__(self, aux_active: bool):
-        self.aux_active = aux_active
+        super().__init__(aux_active)
 
-    def emit_data(self) -> Iterator[int]:
-        # $C054 / $C055 soft-switch steers later writes to MAIN / AUX memory
-        yield 0x55 if self.aux_active else 0x54
-        yield 0xff  # pads out the TCP frame
-
-    def __data_eq__(self, other):
-        return self.aux_active == other.aux_active
+    def _payload(self):
+        return (0x55 if self.aux_active else 0x54, 0xff)
 
 
 class BaseTick(Opcode):
-    """Base class for "fat" audio + video opcode: one per (speaker duty cycle, HiRes
-    page); stores the content byte at 4 offsets of that page."""
+    """"Fat" audio + video opcode, one class per (speaker duty cycle, HiRes page): stores
+    the content byte at four offsets of that page."""
+    FIELDS = ("content", "offsets")
 
     def __init__(self, content: int, offsets: Tuple):
-        self.content = content
         if len(offsets) != 4:
             raise ValueError("Wrong number of offsets: %d != 4" % len(offsets))
-        self.offsets = offsets
+        super().__init__(content, offsets)
 
-    def __data_eq__(self, other):
-        return self.content == other.content and self.offsets == other.offsets
-
-    def emit_data(self):
-        yield self.content
-        yield from self.offsets
+    def _payload(self):
+        return (self.content,) + tuple(self.offsets)
 
 
 TICK_OPCODES = {
