@@ -6,6 +6,7 @@ The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
 
 import os
+import shlex
 import subprocess
 import sys
 
@@ -18,6 +19,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "-Xcompiler", "-Wall"]
 PER_FILE = {"iiv_lut.cu": ["-fmad=false"]}
+# development only: extra nvcc flags (e.g. -DIIV_... experiment switches) for a --force build
+EXTRA = shlex.split(os.environ.get("IIV_NVCC_FLAGS", ""))
 
 
 def _nvcc() -> str:
@@ -48,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         op = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(op)
         if force or _stale(op, [sp] + headers):
-            cmd = [nvcc, *ARCH, *COMMON, *PER_FILE.get(src, []), "-c", sp, "-o", op]
+            cmd = [nvcc, *ARCH, *COMMON, *PER_FILE.get(src, []), *EXTRA, "-c", sp, "-o", op]
             if verbose:
                 cmd.insert(1, "-Xptxas")
                 cmd.insert(2, "-v")

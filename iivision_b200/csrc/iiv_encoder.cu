@@ -32,6 +32,9 @@
 #include <mutex>
 
 #include "iiv_common.cuh"
+#ifdef IIV_X_TIMING
+#include <cstdio>
+#endif
 
 namespace iiv {
 namespace {
@@ -45,7 +48,10 @@ constexpr int kFronts = 2;               // front-end warps of the opcode loop
 // the record is used (8 measured 1-2 % slower, 2 starves the decision warp)
 constexpr int kRecRing = 4;
 constexpr int kOpQueue = 64;            // emitted opcodes waiting for their stores
-constexpr int kRing = 16;               // prefetched delta rows in flight
+// prefetched delta rows in flight: a multiple of the 2 * kProducers entries the producers
+// take per round, so that the entries that share a ring slot (e, e + kRing, ...) all belong
+// to the same producer warp, which writes them in program order
+constexpr int kRing = 18;
 constexpr int kPyBlocks = 4;            // resident 624-word blocks of stream P (power of 2)
 constexpr int kCells = 32 * 256;       // one bank: 32 pages x 256 offsets
 constexpr int kCols = 32 * 128;
@@ -84,7 +90,6 @@ struct Smem {
   // consumer's own (re-queued cells are scored on demand).
   alignas(16) uint16_t ring_row[kRing + 1][256];
   uint32_t ring_tag[kRing];       // sorted-array index the slot holds
-  uint32_t ring_claim[kRing];     // 1 + newest entry that has written (or is writing) the slot
   // top byte of the tempered words of stream P (= getrandbits(8), video.py:178, :291):
   // slot s < kPyBlocks holds the block whose number is s (mod kPyBlocks), the last slot
   // repeats slot 0, so that the bytes of the current block and of its successor are
@@ -110,14 +115,15 @@ struct Smem {
   alignas(16) uint32_t rec[kRecRing][4];
   // (next record number to be popped) << 14 | sorted-heap cursor of that pop: one word, so
   // that turn and cursor cannot be seen out of step
-  volatile uint32_t pop_state;
-  volatile int b_done;            // records the decision warp has finished with
-  volatile int final_emitted;     // total records of the segment (set before stop)
-  volatile int applied_pub;       // records applied so far
-  volatile int head;              // heap entries the consumer is done with
-  volatile int stop;              // segment finished: producers leave
-  volatile int mt_req, mt_done;   // stream P block twists requested / finished
-  volatile int np_pre;            // successor blocks of stream N prepared during phase B
+  // (the words below are shared between warps without a barrier: ld_* / st_* helpers only)
+  uint32_t pop_state;
+  int b_done;            // records the decision warp has finished with
+  int final_emitted;     // total records of the segment (set before stop)
+  int applied_pub;       // records applied so far
+  int head;              // heap entries the consumer is done with
+  int stop;              // segment finished: producers leave
+  int mt_req, mt_done;   // stream P block twists requested / finished
+  int np_pre;            // successor blocks of stream N prepared during phase B
 };
 
 __device__ __forceinline__ void twist(const uint32_t* __restrict__ s,
@@ -181,17 +187,77 @@ __device__ __forceinline__ void warp_twist(const uint32_t* __restrict__ s,
   __syncwarp();
 }
 
-// 16-byte volatile shared-memory load (CUDA C++ has no volatile vector loads): data that
-// another warp publishes.  Being volatile in PTX as well, ptxas keeps it where it is -- a
-// plain ld.shared in an asm statement is fair game for hoisting above a spin loop, however
-// the statement is decorated.
-__device__ __forceinline__ uint4 lds_v4(const void* p) {
-  uint4 v;
-  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "r"((uint32_t)__cvta_generic_to_shared(p))
-               : "memory");
+// ---- cross-warp hand-offs of phase B, on the PTX memory model --------------------------
+// Every word that one warp writes while another may read it is accessed with a strong
+// (.relaxed / .acquire / .release, scope .cta) operation: a flag is published with a release
+// and polled with an acquire, and what sits behind it may then be read with plain loads.
+// On sm_100a an acquire or relaxed load of shared memory is a plain LDS and a relaxed store
+// a plain STS -- the qualifiers only bind ptxas, which may otherwise hoist a load above the
+// spin loop that guards it (it has) -- while a release is MEMBAR.ALL.CTA + STS.
+__device__ __forceinline__ uint32_t smem_addr(const volatile void* p) {
+  return (uint32_t)__cvta_generic_to_shared(const_cast<const void*>(p));
+}
+__device__ __forceinline__ uint32_t ld_acq_u32(const volatile void* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr(p)) : "memory");
   return v;
+}
+__device__ __forceinline__ uint32_t ld_rlx_u32(const volatile void* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_rlx_u16(const volatile void* p) {
+  uint16_t v;
+  asm volatile("ld.relaxed.cta.shared.u16 %0, [%1];" : "=h"(v) : "r"(smem_addr(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_rlx_u64(const volatile void* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_addr(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_acq_v4(const volatile void* p) {
+  uint4 v;
+  asm volatile("ld.acquire.cta.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_rlx_v4(const volatile void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.cta.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_rel_u32(volatile void* p, uint32_t v) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_addr(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_rlx_u32(volatile void* p, uint32_t v) {
+  asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"(smem_addr(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_rlx_u16(volatile void* p, uint16_t v) {
+  asm volatile("st.relaxed.cta.shared.u16 [%0], %1;" ::"r"(smem_addr(p)), "h"(v) : "memory");
+}
+__device__ __forceinline__ void st_rlx_u64(volatile void* p, unsigned long long v) {
+  asm volatile("st.relaxed.cta.shared.u64 [%0], %1;" ::"r"(smem_addr(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_rel_v4(volatile void* p, uint4 v) {
+  asm volatile("st.release.cta.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+               ::"r"(smem_addr(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_rlx_v4(volatile void* p, uint4 v) {
+  asm volatile("st.relaxed.cta.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+               ::"r"(smem_addr(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// fence.acq_rel.cta (MEMBAR.ALL.CTA): with a relaxed store after it, a release pattern on
+// every word stored later in program order (PTX memory model, release patterns, case 3)
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+// a slot lock of the row ring: acquire on taking it, release on giving it back
+__device__ __forceinline__ uint32_t cas_acq_u32(volatile void* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.acquire.cta.shared.cas.b32 %0, [%1], %2, %3;"
+               : "=r"(old) : "r"(smem_addr(p)), "r"(cmp), "r"(val) : "memory");
+  return old;
 }
 
 // getrandbits(8) bytes of one block of stream P into its slot(s) of py_nonce.
@@ -708,7 +774,6 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     constexpr uint32_t kKindLive = 0u, kKindDead = 1u, kKindEndOfHeap = 2u;
     if (t < kRing) {
       sm.ring_tag[t] = 0xffffffffu;
-      sm.ring_claim[t] = 0;
     }
     if (t < kRecRing) *reinterpret_cast<uint4*>(sm.rec[t]) = make_uint4(0u, 0u, 0u, 0u);
     if (t == 0) {
@@ -729,23 +794,24 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     bool out_of_work = false;
     const long long clk_b = clock64();
     long long wait_rows = 0, wait_misc = 0, wait_mt = 0;   // decision-warp stall cycles (diagnostics)
-    volatile uint32_t* tags = sm.ring_tag;
+    uint32_t* tags = sm.ring_tag;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     // Candidate analysis of the 8 offsets a lane owns on `page` for the entry at
     // `cell` whose row of new diffs is `row`: candidate bits (delta < 0, video.py:283),
     // eligibility bits (priority != 0, video.py:159), nonce rank of the lane's first
     // candidate, key prefixes, and the page's candidate count.
-    // `after` is a zero the caller derived from words it has just polled: adding it to
-    // every address makes these loads depend on those, which pins their order.
+    // The caller has acquired the row (its tag) and, in a front end, sampled b_done before:
+    // the page's words race with the decision warp's stores by design -- relaxed loads --
+    // and a record digested from a page that has changed since is caught by the window check.
     auto digest = [&](int cell, const uint16_t* row, uint32_t (&khi)[8], uint32_t& m8,
-                      uint32_t& e8, int& rank, int& n_cand, uint32_t after = 0) {
+                      uint32_t& e8, int& rank, int& n_cand) {
       const int page = cell >> 8, off = cell & 255;
-      const int base = page * 256 + 8 * lane + (int)after;
-      const uint4 ndv = lds_v4(row + 8 * lane);
-      const uint4 dwv = lds_v4(&sm.dw[base]);
-      const uint4 pu0 = lds_v4(&sm.prio[base]);
-      const uint4 pu1 = lds_v4(&sm.prio[base + 4]);
+      const int base = page * 256 + 8 * lane;
+      const uint4 ndv = ld_rlx_v4(row + 8 * lane);
+      const uint4 dwv = ld_rlx_v4(&sm.dw[base]);
+      const uint4 pu0 = ld_rlx_v4(&sm.prio[base]);
+      const uint4 pu1 = ld_rlx_v4(&sm.prio[base + 4]);
       const int4 pr0 = make_int4((int)pu0.x, (int)pu0.y, (int)pu0.z, (int)pu0.w);
       const int4 pr1 = make_int4((int)pu1.x, (int)pu1.y, (int)pu1.z, (int)pu1.w);
       const uint32_t nd[8] = {ndv.x & 0xffffu, ndv.x >> 16, ndv.y & 0xffffu, ndv.y >> 16,
@@ -782,7 +848,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         const int idx = cursor + lane;
         bool live = false;
         if (idx < n_first)
-          live = reinterpret_cast<volatile int32_t*>(sm.prio)[(int)(sm.keys[idx] & 0x1fffu)] != 0;
+          live = ld_rlx_u32(&sm.prio[(int)(sm.keys[idx] & 0x1fffu)]) != 0;
         const uint32_t bal = __ballot_sync(kFull, live);   // video.py:130
         if (bal) return cursor + __ffs(bal) - 1;
         cursor += 32;
@@ -795,7 +861,16 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       int r = 0;                 // next front-end record
       bool heap_done = false;    // sorted heap exhausted: re-queued cells only
       uint32_t hist = 0xffu;     // lane l < 16: page of the record r' = l (mod 16) decided last
+#ifdef IIV_X_TIMING
+      long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      int tcnt[4] = {0, 0, 0, 0};     // settled, contenders, redigest, dead
+      long long tprev = clock64();
+#define IIV_T(k) { const long long tn = clock64(); tacc[k] += tn - tprev; tprev = tn; }
+#else
+#define IIV_T(k)
+#endif
       while (emitted < budget) {
+        IIV_T(0)
         // ---- stream P bookkeeping: kPyBlocks resident 624-word blocks ------------------
         // Moving on to block c frees the slot of block c - 1, into which the twister makes
         // block c + 3 (request number = blocks left behind).  Reads run over into block
@@ -807,14 +882,15 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             const long long c0 = clock64();
             // the twister shares this warp's scheduler: sleep rather than spin, or the
             // poll starves the very warp it is waiting for
-            while ((mt_seen = sm.mt_done) < mt_issued - 1) __nanosleep(40);
-            __threadfence_block();    // the block's nonce bytes are read after the flag
+            // acquire: the block's nonce bytes are read after the flag
+            while ((mt_seen = (int)ld_acq_u32(&sm.mt_done)) < mt_issued - 1) __nanosleep(40);
             wait_mt += clock64() - c0;
           }
           py_cur = (py_cur + 1) & (kPyBlocks - 1);
           pos_py -= 624;
           ++mt_issued;
-          if (lane == 0) sm.mt_req = mt_issued;
+          // release: this warp's reads of the block being replaced come first
+          if (lane == 0) st_rel_u32(&sm.mt_req, (uint32_t)mt_issued);
         }
         const uint8_t* nonces = sm.py_nonce + py_cur * 624 + pos_py;
 
@@ -826,24 +902,27 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           // ---- next record of the front ends -------------------------------------------
           const int rs = r % kRecRing;
           const uint32_t seq = (uint32_t)(r + 1) & 0xffffu;
-          uint4 rec = lds_v4(sm.rec[rs]);
+          uint4 rec = ld_acq_v4(sm.rec[rs]);
           if ((rec.x >> 16) != seq) {
             const long long c0 = clock64();
             do {
-              rec = lds_v4(sm.rec[rs]);
+              rec = ld_acq_v4(sm.rec[rs]);
             } while ((rec.x >> 16) != seq);
             wait_rows += clock64() - c0;
           }
+          IIV_T(1)
           const uint32_t kind = (rec.x >> 14) & 3u;
           if (kind == kKindEndOfHeap) {
             heap_done = true;
-            if (lane == 0) sm.head = n_first;
+            if (lane == 0) st_rlx_u32(&sm.head, (uint32_t)n_first);
           } else {
             const int e = (int)(rec.x & 0x3fffu);
             cell = (int)(rec.y & 0x1fffu);
             content = (rec.y >> 13) & 0xffu;
             slot = e % kRing;
-            if (lane == 0) sm.head = e;
+            // entries before e are done with: their rows were last read before the fence
+            // that preceded the latest b_done store (release pattern on this word too)
+            if (lane == 0) st_rlx_u32(&sm.head, (uint32_t)e);
             // valid unless a record decided after the front end's read hit this page
             const int since = (int)((rec.z >> 22) & 15u);     // records decided since then
             const bool in_window = (lane < 16) & (((r - 1 - lane) & 15) < since);
@@ -857,25 +936,22 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
               n_cont = (int)n_cont_rec;
               settled = rec.z;
               settled_p = rec.w;
-              // the contenders were stored before the record word; the address depends on
-              // the word just loaded (its two top bits are zero), which pins the order of
-              // the two loads whatever the optimisers think of volatile
-              if (!((settled >> 26) & 1u))
-                cont = reinterpret_cast<volatile uint32_t*>(sm.rec_cont[rs] + (rec.y >> 30))[lane];
+              // the contenders were stored before the record word was released
+              if (!((settled >> 26) & 1u)) cont = sm.rec_cont[rs][lane];
               have = true;
-            } else if (reinterpret_cast<volatile int32_t*>(sm.prio)[cell] != 0) {
+            } else if (ld_rlx_u32(&sm.prio[cell]) != 0) {
               redigest = true;     // below, at the one call site this warp has
               have = true;
+              // a settled record is published relaxed (it carries all it needs): acquire
+              // the row from its producer here
+              (void)ld_acq_u32(&tags[slot]);
             }
             // else: the cell was zeroed meanwhile -- it would be popped and skipped
             if (lane == ((r & 15))) hist = have ? (uint32_t)(cell >> 8) : 0xffu;
             ++r;
             if (!have) {
               __syncwarp();
-              if (lane == 0) {
-                __threadfence_block();
-                sm.b_done = r;
-              }
+              if (lane == 0) st_rel_u32(&sm.b_done, (uint32_t)r);
               continue;
             }
           }
@@ -919,7 +995,12 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           __syncwarp();
           redigest = true;
         }
+        IIV_T(2)
+#ifdef IIV_X_TIMING
+        if (redigest) ++tcnt[2]; else if ((settled >> 26) & 1u) ++tcnt[0]; else ++tcnt[1];
+#endif
         if (redigest) digest(cell, sm.ring_row[slot], khi, m8, e8, rank, n_cand);
+        IIV_T(3)
         const int page = cell >> 8, off = cell & 255;
         if (MODE == IIV_MODE_DHGR && content >= 0x80u) error_flags |= 1;  // :137
 
@@ -991,18 +1072,18 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           p2 = sm.ring_row[slot][o2];
         }
         }
+        IIV_T(4)
         int push1 = p1 != 0, push2 = p2 != 0;
         if (n_pushed + push1 + push2 > pushed_cap) {   // the host sizes the overflow list so
           error_flags |= 4;                            // that this cannot happen
           push1 = push2 = 0;
         }
         if (lane == 0) {
-          // volatile: these stores must stay ahead of the b_done store below
-          volatile int32_t* vprio = sm.prio;
-          vprio[cell] = 0;                                             // video.py:140
-          reinterpret_cast<volatile uint16_t*>(sm.dw)[cell] = 0;      // video.py:141
-          if (has1) vprio[page * 256 + o1] = (int32_t)p1;            // video.py:170
-          if (has2) vprio[page * 256 + o2] = (int32_t)p2;
+          // relaxed: the front ends and producers read these words while they change
+          st_rlx_u32(&sm.prio[cell], 0u);                                  // video.py:140
+          st_rlx_u16(&sm.dw[cell], 0);                                     // video.py:141
+          if (has1) st_rlx_u32(&sm.prio[page * 256 + o1], p1);            // video.py:170
+          if (has2) st_rlx_u32(&sm.prio[page * 256 + o2], p2);
           if (push1) {   // video.py:173-178
             const uint64_t key = requeue_key(p1, push_nonce0, page * 256 + o1);
             if (n_pushed < kPushedCap) sm.pushed[n_pushed] = key;
@@ -1020,32 +1101,44 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           rec.x = (uint32_t)(page + 32) | (content << 8) | ((uint32_t)off << 16) |
                   ((uint32_t)o1 << 24);
           rec.y = (uint32_t)o2 | ((uint32_t)off << 8) | (1u << 16);
-          *reinterpret_cast<uint2*>(seg_out + (size_t)emitted * 8) = rec;
+          const uint2 rec_out = rec;
+          *reinterpret_cast<uint2*>(seg_out + (size_t)emitted * 8) = rec_out;
           // hand the stores to the applier (video.py:144, :172); the queue is checked
           // for room once per 16 records
-          if ((emitted & 15) == 0 && emitted - sm.applied_pub > kOpQueue - 16) {
+          if ((emitted & 15) == 0 &&
+              emitted - (int)ld_acq_u32(&sm.applied_pub) > kOpQueue - 16) {
             const long long c0 = clock64();
-            while (emitted - sm.applied_pub > kOpQueue - 16) {}
+            // the applier runs on another scheduler; back off all the same
+            while (emitted - (int)ld_acq_u32(&sm.applied_pub) > kOpQueue - 16) __nanosleep(20);
             wait_misc += clock64() - c0;
           }
           rec.y |= (uint32_t)((emitted + 1) & 255) << 24;
-          reinterpret_cast<volatile unsigned long long*>(sm.opq)[emitted % kOpQueue] =
-              ((unsigned long long)rec.y << 32) | rec.x;
-          // the priorities above are in place: later front-end reads see this opcode.  One
-          // thread's shared-memory stores are performed in program order; the barrier only
-          // keeps the compiler from sinking the plain stores below the volatile one.
-          asm volatile("" ::: "memory");
-          if (!heap_done) sm.b_done = r;
+          // one word, its own ready flag (sequence number in the top byte)
+          st_rlx_u64(&sm.opq[emitted % kOpQueue], ((unsigned long long)rec.y << 32) | rec.x);
+          // the priorities above are in place: whoever sees this b_done sees them, and what
+          // this warp read of the record's row and contenders came first
+          if (!heap_done) {
+            fence_cta();
+            st_rlx_u32(&sm.b_done, (uint32_t)r);
+          }
         }
+        IIV_T(5)
         n_pushed += push1 + push2;
         pos_py += n_cand + push1 + push2;
         py_words += n_cand + push1 + push2;
         ++emitted;
         __syncwarp();
+        IIV_T(6)
       }
-      while (mt_seen < mt_issued) mt_seen = sm.mt_done;
+#ifdef IIV_X_TIMING
+      if (lane == 0 && clip == 0)
+        printf("seg %d emitted %d | top %lld recwait %lld classify %lld digest %lld winners %lld stores %lld sync %lld | settled %d cont %d redigest %d\n",
+               seg, emitted, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6],
+               tcnt[0], tcnt[1], tcnt[2]);
+#endif
+      while (mt_seen < mt_issued) mt_seen = (int)ld_acq_u32(&sm.mt_done);
       if (lane == 0) {
-        sm.final_emitted = emitted;
+        st_rlx_u32(&sm.final_emitted, (uint32_t)emitted);
         sm.wmin64[0] = (uint64_t)wait_rows;
         sm.wmin64[1] = (uint64_t)(wait_misc + wait_mt);
         sm.wmin64[2] = (uint64_t)(clock64() - clk_b);
@@ -1055,8 +1148,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         sm.scan[3] = pos_py;
         sm.scan[4] = py_cur;
         sm.scan[5] = error_flags;
-        __threadfence_block();
-        sm.stop = 1;
+        st_rel_u32(&sm.stop, 1u);      // final_emitted is in place for whoever sees it
       }
     } else if (warp == kDecideWarp - 1 || warp == kDecideWarp - 2) {
       // ---- front end: records r = f, f + 2, ... ----------------------------------------
@@ -1066,12 +1158,14 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         bool quit = false;
         uint32_t pop = 0;
         while (true) {
-          if (sm.stop) {
+          if (ld_rlx_u32(&sm.stop)) {
             quit = true;
             break;
           }
-          pop = sm.pop_state;
-          if ((int)(pop >> 14) == r && r < sm.b_done + kRecRing) break;
+          pop = ld_rlx_u32(&sm.pop_state);
+          // acquire: record slot r % kRecRing (word and contenders) is rewritten below, after
+          // the decision warp's reads of record r - kRecRing
+          if ((int)(pop >> 14) == r && r < (int)ld_acq_u32(&sm.b_done) + kRecRing) break;
           __nanosleep(20);
         }
         if (quit) break;
@@ -1081,15 +1175,17 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         if (e < 0) {
           // heap exhausted: tell the decision warp, and let the other front end see it too
           if (lane == 0) {
-            *reinterpret_cast<uint4*>(sm.rec[rs]) =
-                make_uint4(seq | (kKindEndOfHeap << 14), 0u, 0u, 0u);
-            sm.pop_state = ((uint32_t)(r + 1) << 14) | (pop & 0x3fffu);
+            st_rlx_v4(sm.rec[rs], make_uint4(seq | (kKindEndOfHeap << 14), 0u, 0u, 0u));
+            st_rlx_u32(&sm.pop_state, ((uint32_t)(r + 1) << 14) | (pop & 0x3fffu));
           }
           break;
         }
         const int cell = (int)(sm.keys[e] & 0x1fffu);
-        const int seen = sm.b_done;      // BEFORE the page is read (fence below)
-        if (lane == 0) sm.pop_state = ((uint32_t)(r + 1) << 14) | (uint32_t)(e + 1);
+        // sampled BEFORE the page is read (an acquire keeps the later loads behind it): every
+        // opcode that can have changed the page since is then inside the window the decision
+        // warp checks
+        const int seen = (int)ld_acq_u32(&sm.b_done);
+        if (lane == 0) st_rlx_u32(&sm.pop_state, ((uint32_t)(r + 1) << 14) | (uint32_t)(e + 1));
         // the row of this entry, from the producers.  If the cell has been zeroed since the
         // probe (by an opcode decided meanwhile) nobody may ever score it: hand over a
         // dead record, which the decision warp drops like the pop-and-skip it stands for.
@@ -1097,7 +1193,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         uint32_t tag = 0;
         bool dead = false;
         while (true) {
-          if (reinterpret_cast<volatile int32_t*>(sm.prio)[cell] == 0) {
+          if (ld_rlx_u32(&sm.prio[cell]) == 0) {
             dead = true;
             break;
           }
@@ -1105,10 +1201,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           // Once every earlier record has been decided this entry is the oldest one in
           // use, however many dead entries precede it -- move the window up to it, or
           // nobody would ever score it.
-          if (lane == 0 && sm.b_done == r) sm.head = e;
-          tag = tags[slot];
+          if (lane == 0 && (int)ld_acq_u32(&sm.b_done) == r) st_rlx_u32(&sm.head, (uint32_t)e);
+          tag = ld_acq_u32(&tags[slot]);       // acquire: the row is read after its tag
           if ((tag >> 8) == (uint32_t)e) break;
-          if (sm.stop) {
+          if (ld_rlx_u32(&sm.stop)) {
             quit = true;
             break;
           }
@@ -1116,19 +1212,16 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         if (quit) break;
         if (dead) {
           if (lane == 0)
-            *reinterpret_cast<uint4*>(sm.rec[rs]) = make_uint4(
-                seq | (kKindDead << 14) | (uint32_t)e, (uint32_t)cell, 0u, 0u);
+            st_rlx_v4(sm.rec[rs], make_uint4(seq | (kKindDead << 14) | (uint32_t)e,
+                                             (uint32_t)cell, 0u, 0u));
           continue;
         }
-        // The row must be read after its tag and the page after `seen`.  A fence here costs
-        // 5 % of a clip's time, so the order is pinned by address dependencies instead: a
-        // tag is below 2^21 and `seen` is not negative, which makes `after` zero -- but only
-        // once both words have been loaded.
-        const uint32_t after = (tag >> 24) | ((uint32_t)seen >> 31);
-        const uint16_t* row = sm.ring_row[slot] + after;
+        // The row is read after its tag and the page after `seen`: both were acquire loads
+        // (plain LDS on this part; a fence here cost 5 % of a clip's time).
+        const uint16_t* row = sm.ring_row[slot];
         uint32_t khi[8], m8, e8;
         int rank, n_cand;
-        digest(cell, row, khi, m8, e8, rank, n_cand, after);
+        digest(cell, row, khi, m8, e8, rank, n_cand);
         // Whatever the nonces, the two winners have one of the two smallest deltas among
         // the competing candidates: pass only those on (with their nonce ranks).
         const uint32_t use8 = m8 & e8;
@@ -1166,13 +1259,13 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           if (g1 != 0xffffffffu) {
             const uint32_t w1 = g1 & 255u;
             settled |= w1 | (1u << 27);
-            settled_p = reinterpret_cast<const volatile uint16_t*>(row)[w1];
+            settled_p = row[w1];
             n_cont = 1;
           }
           if (g2 != 0xffffffffu) {
             const uint32_t w2 = g2 & 255u;
             settled |= (w2 << 8) | (1u << 28);
-            settled_p |= (uint32_t)reinterpret_cast<const volatile uint16_t*>(row)[w2] << 16;
+            settled_p |= (uint32_t)row[w2] << 16;
             n_cont = 2;
           }
         } else {
@@ -1209,15 +1302,19 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             }
           }
         }
-        // the contenders (all lanes), if any, go first, then the record word
+        // the contenders (all lanes), if any, go first, then the record word: a release when
+        // something sits behind it (the contenders; the row, which the decision warp then
+        // reads on the strength of this warp's acquire of its tag), relaxed when the word is
+        // all there is
         __syncwarp();
         if (lane == 0) {
-          if (!settled) __threadfence_block();
-          *reinterpret_cast<uint4*>(sm.rec[rs]) = make_uint4(
+          const uint4 word = make_uint4(
               seq | (kKindLive << 14) | (uint32_t)e,
               (uint32_t)cell | ((tag & 0xffu) << 13) | ((uint32_t)n_cand << 21),
               settled | ((uint32_t)min(n_cont, 63) << 16) | ((uint32_t)(r - seen) << 22),
               settled_p);
+          if (settled) st_rlx_v4(sm.rec[rs], word);
+          else st_rel_v4(sm.rec[rs], word);
         }
       }
     } else if (warp < kProducers) {
@@ -1228,8 +1325,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         while (true) {
           int h = 0, st = 0;
           if (lane == 0) {
-            h = sm.head;
-            st = sm.stop;
+            h = (int)ld_acq_u32(&sm.head);     // acquire: rows of entries before h are free
+            st = (int)ld_rlx_u32(&sm.stop);
           }
           h = __shfl_sync(kFull, h, 0);
           st = __shfl_sync(kFull, st, 0);
@@ -1243,44 +1340,29 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         if (quit) break;
         const int cell0 = (int)(sm.keys[e0] & 0x1fffu);
         const int cell1 = e1 < n_first ? (int)(sm.keys[e1] & 0x1fffu) : cell0;
-        const volatile int32_t* vprio = reinterpret_cast<volatile int32_t*>(sm.prio);
-        const bool alive0 = vprio[cell0] != 0;
-        const bool alive1 = e1 < n_first && vprio[cell1] != 0;
+        const bool alive0 = ld_rlx_u32(&sm.prio[cell0]) != 0;
+        const bool alive1 = e1 < n_first && ld_rlx_u32(&sm.prio[cell1]) != 0;
         uint32_t c0 = 0, c1 = 0;
         if (alive0) c0 = __ldg(tmem + cell0);
         if (alive1) c1 = __ldg(tmem + cell1);
-        // Rows are scored into registers first and stored only while the entry is still
-        // inside the ring window.  A producer can fall a whole ring revolution behind on an
-        // entry that died after its aliveness check (nobody waits for such a row, so the
-        // window moves on); the slot may then already belong to entry e + kRing.  Guards:
-        // (1) the window check -- the newer entry's producer cannot even start scoring
-        // (two dependent global loads) before head has passed e, so a store issued right
-        // after seeing head <= e lands first; (2) the claim word, which keeps a row that is
-        // already newer from being replaced.
+        // Rows are scored into registers first.  A producer can fall a whole ring revolution
+        // behind on an entry that died after its aliveness check (nobody waits for such a
+        // row, so the window moves on), and the slot may then be due for entry e + kRing --
+        // which is this same warp's (kRing is a multiple of the producers' round), a later
+        // iteration of this loop: the rows of a slot are written in entry order, by one warp.
+        static_assert(kRing % (2 * kProducers) == 0, "a ring slot must stay with one producer");
         uint4 row0 = make_uint4(0, 0, 0, 0), row1 = row0;
         if (alive0) row0 = score_row_regs<MODE>(tp + (cell0 >> 8) * 128, table, c0, is_aux, lane);
         if (alive1) row1 = score_row_regs<MODE>(tp + (cell1 >> 8) * 128, table, c1, is_aux, lane);
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-          const bool alive = which ? alive1 : alive0;
-          if (!alive) continue;
-          const int e = which ? e1 : e0;
-          const int slot = e % kRing;
-          const bool mine =
-              sm.head <= e &&
-              reinterpret_cast<volatile uint32_t*>(sm.ring_claim)[slot] <= (uint32_t)e;
-          if (mine) {
-            reinterpret_cast<uint4*>(sm.ring_row[slot])[lane] = which ? row1 : row0;
-            __syncwarp();
-            if (lane == 0) {
-              // after __syncwarp + fence: every lane's row stores are ordered before the tag
-              __threadfence_block();
-              reinterpret_cast<volatile uint32_t*>(sm.ring_claim)[slot] = (uint32_t)e + 1u;
-              tags[slot] = ((uint32_t)e << 8) | (which ? c1 : c0);
-            }
-          }
-          __syncwarp();
+        if (alive0) reinterpret_cast<uint4*>(sm.ring_row[e0 % kRing])[lane] = row0;
+        if (alive1) reinterpret_cast<uint4*>(sm.ring_row[e1 % kRing])[lane] = row1;
+        __syncwarp();      // every lane's row stores, then lane 0's release of the tags
+        if (lane == 0 && (alive0 || alive1)) {
+          fence_cta();     // one fence releases both tags (a fence followed by strong stores)
+          if (alive0) st_rlx_u32(&tags[e0 % kRing], ((uint32_t)e0 << 8) | c0);
+          if (alive1) st_rlx_u32(&tags[e1 % kRing], ((uint32_t)e1 << 8) | c1);
         }
+        __syncwarp();
       }
     } else if (warp == kApplyWarp) {
       // applier: Bitmap.apply for (off, o1, o2) of each published record.  Stores only
@@ -1289,10 +1371,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       // records that share a page go in emission order, one per round.  Re-applying an
       // offset that repeats offsets[0] is idempotent.
       int applied = 0;
-      volatile unsigned long long* q = sm.opq;
       while (true) {
         const int idx = applied + lane;
-        const unsigned long long raw = q[idx % kOpQueue];
+        const unsigned long long raw = ld_rlx_u64(&sm.opq[idx % kOpQueue]);
         const bool ready = (uint32_t)(raw >> 56) == (uint32_t)((idx + 1) & 255) && raw != 0ull;
         // the records form a prefix: lane i can only go if lanes < i are ready as well
         const uint32_t rdy = __ballot_sync(kFull, ready);
@@ -1319,13 +1400,14 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             pending &= pending - 1;
           }
           applied += count;
-          if (lane == 0) sm.applied_pub = applied;
+          // release: the queue slots just read may be rewritten by whoever sees this
+          __syncwarp();
+          if (lane == 0) st_rel_u32(&sm.applied_pub, (uint32_t)applied);
         } else {
           int st = 0, fin = 0;
           if (lane == 0) {
-            st = sm.stop;                 // read before the count: stop is set last
-            __threadfence_block();
-            fin = sm.final_emitted;
+            st = (int)ld_acq_u32(&sm.stop);        // stop is set last, with a release
+            fin = (int)ld_rlx_u32(&sm.final_emitted);
           }
           st = __shfl_sync(kFull, st, 0);
           fin = __shfl_sync(kFull, fin, 0);
@@ -1353,8 +1435,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       while (true) {
         int req = 0, st = 0;
         if (lane == 0) {
-          req = sm.mt_req;
-          st = sm.stop;
+          req = (int)ld_acq_u32(&sm.mt_req);    // acquire: the slot to overwrite has been read
+          st = (int)ld_rlx_u32(&sm.stop);
         }
         req = __shfl_sync(kFull, req, 0);
         st = __shfl_sync(kFull, st, 0);
@@ -1365,16 +1447,15 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           const int src = (dst + kPyBlocks - 1) & (kPyBlocks - 1);
           warp_twist<true>(sm.mt_py[src], sm.mt_py[dst], lane, dst, sm.py_nonce);
           ++done;
-          __threadfence_block();
-          __syncwarp();
-          if (lane == 0) sm.mt_done = done;
+          __syncwarp();     // every lane's words and nonce bytes, then lane 0's release
+          if (lane == 0) st_rel_u32(&sm.mt_done, (uint32_t)done);
         } else if (st) {
           break;
         } else if (np_made < np_goal) {
           warp_twist<false>(np_made == 0 ? sm.mt_np[np_cur] : np_pre_blocks + (np_made - 1) * 624,
                             np_pre_blocks + np_made * 624, lane, 0, sm.py_nonce);
           ++np_made;
-          if (lane == 0) sm.np_pre = np_made;
+          if (lane == 0) st_rlx_u32(&sm.np_pre, (uint32_t)np_made);
         } else if (pf_tp != nullptr && pf_col < kCols) {
           uint64_t g[4];
 #pragma unroll
