@@ -298,22 +298,27 @@ def phase_a_figures(torch, ops, table):
     previous frame's bitmap and folds the priorities."""
     from iivision_b200 import synth
     nb = int(os.environ.get("IIV_BENCH_SCORE_FRAMES", "1024"))
-    fr = synth.synthetic_frames("DHGR", nb + 1, 1.0, seed=1)
-    d = torch.from_numpy(fr).cuda()
-    src = ops.pack("DHGR", d[:nb, 0].contiguous(), d[:nb, 1].contiguous())
-    tgt = d[1:].contiguous()
-    prio = torch.zeros((nb, 2, 32, 256), dtype=torch.int32, device="cuda")
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    for _ in range(3):
-        ops.score_frames("DHGR", src, tgt, table, priority=prio)
-    torch.cuda.synchronize()
-    reps = 20
-    ev[0].record()
-    for _ in range(reps):
-        ops.score_frames("DHGR", src, tgt, table, priority=prio)
-    ev[1].record()
-    torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[1]) / reps
+
+    def timed(fraction):
+        fr = synth.synthetic_frames("DHGR", nb + 1, fraction, seed=1)
+        d = torch.from_numpy(fr).cuda()
+        src = ops.pack("DHGR", d[:nb, 0].contiguous(), d[:nb, 1].contiguous())
+        tgt = d[1:].contiguous()
+        prio = torch.zeros((nb, 2, 32, 256), dtype=torch.int32, device="cuda")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for _ in range(3):
+            ops.score_frames("DHGR", src, tgt, table, priority=prio)
+        torch.cuda.synchronize()
+        reps = 20
+        ev[0].record()
+        for _ in range(reps):
+            ops.score_frames("DHGR", src, tgt, table, priority=prio)
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / reps
+
+    ms = timed(1.0)
+    ms_5pct = timed(0.05)
     peaks, peak_src = measured_peaks()
     # SURVEY 8(d): one diff_weights bank call = 2 x 32 KiB packed in + 32 KiB int32 out +
     # 8192 x 2 B of table = 112 KiB algorithmic, 8192 x 32 B = 256 KiB of sectors; a DHGR
@@ -324,23 +329,42 @@ def phase_a_figures(torch, ops, table):
     sector = 2 * 8192 * 32 * nb
     streamed = (16 + 32 + 32 + 64 + 128) * 1024 * nb
     achieved = alg / (ms * 1e-3) / 1e9
+    # DRAM bytes of one launch of 1024 noise frames from the committed ncu capture
+    # (profiles/r02a_score_frames_ncu_summary.txt: dram__bytes_read 1.8425 GB +
+    # dram__bytes_write 0.1609 GB): 93 B cross the DRAM pins per 2-byte gather
+    traffic = (1.842528e9 + 0.160930e9) * nb / 1024
     return {
         "scored_frames_per_s": nb / (ms * 1e-3),
+        "scored_frames_per_s_5pct_change": nb / (ms_5pct * 1e-3),
+        "scored_5pct_note": "same launch on frames that re-draw 5 % of the bytes of their "
+                            "predecessor (synth fraction 0.05) instead of all of them: the "
+                            "unchanged bytes gather from the tables' diagonals",
         "scored_frames_note": (
             "iiv_score_frames: pack + diff_weights (main+aux) + hole mask + priority fold of "
             "%d DISTINCT DHGR frames per launch (source = the previous frame), device "
             "resident; %.1f MB streamed per launch (> L2) + %d random table gathers" % (
                 nb, streamed / 1e6, 2 * 8192 * nb)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                     "traffic_gbs": traffic / (ms * 1e-3) / 1e9,
+                     "traffic_frac_of_peak": traffic / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "gathers_per_s": 2 * 8192 * nb / (ms * 1e-3),
+                     "bare_gather_ceiling_per_s": 57.8e9,
                      "peak_source": peak_src, "kernel": "score_frames_kernel",
                      "kernel_ms": ms, "algorithmic_bytes_per_launch": alg,
                      "gather_sector_bytes_per_launch": sector,
                      "streamed_bytes_per_launch": streamed,
                      "sector_plus_streamed_gbs": (sector + streamed) / (ms * 1e-3) / 1e9,
                      "note": "algorithmic = 112 KiB per bank call (SURVEY 8(d)) x 2 banks x "
-                             "frames; the gathers are uniform over the 512 MiB table (random "
-                             "frames), each costing a 32 B sector"},
+                             "frames; the gathers are uniform over the 512 MiB table (noise "
+                             "frames: the worst case), each a 32 B sector of L2 traffic and, "
+                             "measured, 93 B of DRAM traffic (traffic = dram bytes of the "
+                             "committed ncu capture scaled to this launch).  By DRAM bytes "
+                             "the kernel runs at traffic_frac_of_peak of the copy peak, and at "
+                             "gathers_per_s against the 57.8 G/s of a bare 16-per-thread "
+                             "random-gather loop over the same table "
+                             "(profiles/r02_gather_flavours.txt): DRAM row activations, not "
+                             "bytes, bound it"},
     }
 
 

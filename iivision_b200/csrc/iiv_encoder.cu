@@ -372,13 +372,15 @@ __device__ __forceinline__ void apply_store(uint64_t* src, uint8_t* mem, int pag
                                             int offset, int is_aux, uint32_t value) {
   const int o = byte_offset<MODE>(offset, is_aux);
   const int c = offset >> 1;
+  // relaxed stores: the applier is the only writer in phase B, but the twister reads these
+  // words (for prefetch addresses only) while they change
   uint64_t* row = src + page * 128;
   const uint64_t w = masked_update<MODE>(o, row[c], value);
-  row[c] = w;
+  st_rlx_u64(&row[c], w);
   if (o == 0 && c > 0)
-    row[c - 1] = (row[c - 1] & keep_low_mask<MODE>()) ^ footer_of<MODE>(w);
+    st_rlx_u64(&row[c - 1], (row[c - 1] & keep_low_mask<MODE>()) ^ footer_of<MODE>(w));
   else if (o == Mode<MODE>::kOffsets - 1 && c < 127)
-    row[c + 1] = (row[c + 1] & keep_high_mask<MODE>()) ^ header_of<MODE>(w);
+    st_rlx_u64(&row[c + 1], (row[c + 1] & keep_high_mask<MODE>()) ^ header_of<MODE>(w));
   mem[page * 256 + offset] = (uint8_t)value;
 }
 
@@ -1462,7 +1464,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           for (int q = 0; q < 4; ++q) g[q] = __ldg(pf_tp + pf_col + 32 * q + lane);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint64_t s = sm.src[pf_col + 32 * q + lane];
+            const uint64_t s = ld_rlx_u64(&sm.src[pf_col + 32 * q + lane]);   // racy by design
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const int o = byte_offset<MODE>(half, pf_aux);

@@ -267,13 +267,37 @@ def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,
                              stream.numel(), crc, pieces)
 
 
-def main():
-    os.makedirs(DATA_DIR, mode=0o755, exist_ok=True)
+def table_jobs():
+    """The files make_data_tables.main() writes (make_data_tables.py:191-204), in its order:
+    (palette, bitmap class, nominal colours, relative cost = table bytes)."""
+    jobs = []
     for p in palette.PALETTES.values():
-        print("Processing palette %s" % p)
-        edp = compute_substitute_costs(p)
-        make_edit_distance(p, edp, screen.HGRBitmap, colours.HGRColours)
-        make_edit_distance(p, edp, screen.DHGRBitmap, colours.DHGRColours)
+        jobs.append((p, screen.HGRBitmap, colours.HGRColours, 2.0))
+        jobs.append((p, screen.DHGRBitmap, colours.DHGRColours, 1.0))
+    return jobs
+
+
+def main(rank: int = None, world: int = None):
+    """All table files.  Under torchrun (RANK / WORLD_SIZE set, or given) the files are
+    independent jobs and are shared out over the ranks, one GPU each; nothing is exchanged."""
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    os.makedirs(DATA_DIR, mode=0o755, exist_ok=True)
+    jobs = table_jobs()
+    mine = range(len(jobs))
+    if world > 1:
+        from . import parallel
+        mine = parallel.shard_jobs([j[3] for j in jobs], world, rank)
+    edps = {}
+    written = []
+    for k in mine:
+        p, bitmap_cls, nominal, _ = jobs[k]
+        if p not in edps:
+            print("Processing palette %s" % p)
+            edps[p] = compute_substitute_costs(p)
+        make_edit_distance(p, edps[p], bitmap_cls, nominal)
+        written.append("%s/%s_palette_%d_edit_distance.npz" % (DATA_DIR, bitmap_cls.NAME, p.ID.value))
+    return written
 
 
 if __name__ == "__main__":

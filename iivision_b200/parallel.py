@@ -55,6 +55,22 @@ def triangle_row_blocks(n_rows: int, world: int, rank: int) -> List[Tuple[int, i
     return [(lo * step, (lo + 1) * step), (hi * step, (hi + 1) * step)]
 
 
+def shard_jobs(costs, world: int, rank: int) -> List[int]:
+    """Indices of the independent jobs (table files) of one rank: longest job first, each to
+    the rank with the least work so far (ties: the lower rank).  Every rank computes the
+    same assignment, so no message is needed."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("rank %d of %d" % (rank, world))
+    load = [0.0] * world
+    mine = []
+    for k in sorted(range(len(costs)), key=lambda k: (-float(costs[k]), k)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        load[r] += float(costs[k])
+        if r == rank:
+            mine.append(k)
+    return sorted(mine)
+
+
 def shard_range(n_items: int, world: int, rank: int) -> Tuple[int, int]:
     """Balanced contiguous split of independent items (clips) across ranks."""
     base, extra = divmod(n_items, world)

@@ -281,13 +281,19 @@ class Video:
 
         self._live = None           # the _Run of the generator currently being pulled
         self._spec = None           # _Kernel launched ahead for the predicted next generator
-        self._pulls = 0             # opcodes pulled over this object's life
+        self._pulls_closed = 0      # opcodes pulled from the generators that are closed
         self._host_fresh = True     # host arrays == committed state
         self._touched_at = 0        # value of _pulls when the host arrays were last handed out
         self._touched = True        # ... and they may have been edited since (upload first)
         self._np_mark = None        # global generator states the device copies correspond to
         self._py_mark = None
         self._gauss_next = None
+
+    @property
+    def _pulls(self) -> int:
+        """Opcodes pulled over this object's life."""
+        live = self._live
+        return self._pulls_closed + (live.pulled if live is not None else 0)
 
     def __del__(self):
         if sys is None or sys.is_finalizing():
@@ -541,10 +547,19 @@ class Video:
         try:
             k = 0
             while True:
+                # the opcodes the current kernel run holds, without a call per pull
+                kern = run.kernel
+                rows = kern._ops
+                n = min(kern.real, kern.budget)
+                while k < n:
+                    r = rows[k]
+                    k += 1
+                    run.pulled = k      # the stores of opcode k-1 are committed state
+                    yield r[0], r[1], r[2:6]
+                # past it: re-run with a larger budget, or out of work (padding)
                 op = run.opcode(k)
                 k += 1
-                run.pulled = k      # the stores of opcode k-1 are committed state
-                self._pulls += 1
+                run.pulled = k
                 yield op
         finally:
             run.finish()
@@ -611,10 +626,12 @@ class _Run:
     def opcode(self, k: int):
         kern = self.kernel
         if k >= kern.budget and kern.real == kern.budget:
-            if kern.budget >= MAX_BUDGET:
+            if k >= MAX_BUDGET:
                 raise NotImplementedError(
                     "more than %d opcodes pulled from one encode_frame generator" % MAX_BUDGET)
-            self._rerun(min(max(2 * kern.budget, self.v.speculate), MAX_BUDGET))
+            # (the current run may be shorter than k: sync() settles on exactly the opcodes
+            # pulled while the generator goes on serving the run it started with)
+            self._rerun(min(max(2 * kern.budget, self.v.speculate, k + 1), MAX_BUDGET))
             kern = self.kernel
         if k >= kern.real:
             # out of work: (32, target[0, 0], [0, 0, 0, 0]) forever (video.py:249-251)
@@ -671,6 +688,7 @@ class _Run:
         v = self.v
         if v._live is self:
             v._live = None
+        v._pulls_closed += self.pulled
         if sys.is_finalizing():               # interpreter shutdown: CUDA may be gone
             return
         k = self.pulled

@@ -104,3 +104,18 @@ def test_sharded_table_world2():
     for p in procs:
         p.join(30)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_shard_jobs_balances_and_covers():
+    """Table files are independent jobs: every job goes to exactly one rank, every rank
+    computes the same assignment, and the heaviest rank carries no more than it must."""
+    from iivision_b200 import parallel
+    costs = [2.0, 1.0, 2.0, 1.0]          # HGR / DHGR x two palettes (make_data_tables.main)
+    for world in (1, 2, 3, 4, 8):
+        shares = [parallel.shard_jobs(costs, world, r) for r in range(world)]
+        assert sorted(k for s in shares for k in s) == list(range(len(costs)))
+        loads = [sum(costs[k] for k in s) for s in shares]
+        assert max(loads) == {1: 6.0, 2: 3.0, 3: 2.0, 4: 2.0, 8: 2.0}[world]
+    import pytest
+    with pytest.raises(ValueError):
+        parallel.shard_jobs(costs, 2, 2)
