@@ -41,10 +41,9 @@ PROTOTYPES = {
                                    c_void_p]),
     "iiv_deflate_block_bytes": (c_size_t, []),
     "iiv_deflate_block_stride": (c_size_t, []),
-    "iiv_deflate_survey": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                   c_int, c_void_p]),
-    "iiv_deflate_encode": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "iiv_deflate_survey": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                    c_void_p]),
+    "iiv_deflate_encode": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "iiv_deflate_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "iiv_table_symmetrise": (c_int, [c_int, c_void_p, c_void_p]),
     "iiv_pack": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_int,

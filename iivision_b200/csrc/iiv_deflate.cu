@@ -8,11 +8,12 @@
 // concatenation.  Each of a block's 128 threads parses 256 bytes greedily, byte by byte:
 //   * the longest match of >= 3 bytes among a few candidate distances -- whole entries
 //     back, so only same-half bytes are compared: the previous entry (runs: the zeros
-//     above the diagonal), fixed column distances where these tables repeat (Cands<>), and
-//     the previous COLUMN with the same pixel string (HGR maps 16 384 masked values onto
-//     10 710 strings; d_dup[o][j] = entries back to it, 0 if none).  Matches may start and
-//     end on either byte of an entry: a lone repeated entry between two equal high bytes
-//     is the most frequent match of all;
+//     above the diagonal) and fixed column distances where these tables repeat (Cands<>:
+//     columns that differ in one bit which the row's string happens not to care about --
+//     or not at all: HGR maps 16 384 masked values onto 10 710 pixel strings, and the
+//     columns with equal strings sit 4 or 2048 apart).  Matches may start and end on
+//     either byte of an entry: a lone repeated entry between two equal high bytes is the
+//     most frequent match of all;
 //   * else one literal byte.
 // The Huffman codes come from the host (deflate.py), built from the histogram the survey
 // kernel takes over a sample of the blocks; a block that would not shrink is stored.
@@ -120,23 +121,10 @@ __device__ __forceinline__ uint32_t diff_at(const uint16_t* e, int q, int d) {
   return d <= q ? (uint32_t)e[padded(q)] ^ (uint32_t)e[padded(q - d)] : kNoMatch;
 }
 
-// Distance (in entries) to the previous column with the same pixel string, as a candidate
-// for entry q; a huge distance (never <= q) when there is none.
-__device__ __forceinline__ int dup_at(const uint16_t* __restrict__ dup_row, uint32_t col0,
-                                      uint32_t n_mask, int q) {
-  const uint32_t col = (col0 + (uint32_t)q) & n_mask;
-  const int d = dup_row[col];
-  // d <= col: the earlier column is in the same row, hence inside this block
-  return (d != 0 && (uint32_t)d <= col) ? d : 0x40000000;
-}
-
 // Bytes that repeat the bytes 2 * d earlier, from half `s` (0 = low byte) of entry p up to
 // the end of the thread's chunk.  Distances are whole entries, so a byte is always compared
 // with the same half of an earlier entry: one XOR of two entries answers for both bytes.
-template <bool DUP>
-__device__ __forceinline__ int match_bytes(const uint16_t* e, const uint16_t* __restrict__ dup_row,
-                                           uint32_t col0, uint32_t n_mask, int p, int s,
-                                           int end, int d) {
+__device__ __forceinline__ int match_bytes(const uint16_t* e, int p, int s, int end, int d) {
   uint32_t x = diff_at(e, p, d);
   int len;
   if (s == 0) {
@@ -148,7 +136,6 @@ __device__ __forceinline__ int match_bytes(const uint16_t* e, const uint16_t* __
     len = 1;
   }
   for (int q = p + 1; q < end; ++q) {
-    if (DUP && dup_at(dup_row, col0, n_mask, q) != d) break;
     x = (uint32_t)e[padded(q)] ^ (uint32_t)e[padded(q - d)];
     if (x) {
       len += (x & 0xffu) ? 0 : 1;
@@ -161,54 +148,35 @@ __device__ __forceinline__ int match_bytes(const uint16_t* e, const uint16_t* __
 
 // Walks a thread's 256 bytes greedily and hands every token to the sink: the longest match
 // among the candidate distances when it covers at least three bytes (ties: the nearest),
-// else one literal byte.  Candidates: the fixed distances above and, per column, the
-// previous column with the same pixel string (d_dup).  A match stays inside the thread's
-// chunk; its source may lie anywhere earlier in the block.
+// else one literal byte.  A match stays inside the thread's chunk; its source may lie
+// anywhere earlier in the block.
 //   sink.lit(byte);  sink.match(length in bytes, distance in bytes)
 // The XORs of the current entry (xp) and the next (xn) against every candidate stay in
 // registers: a match of three bytes from the low byte needs xp == 0 and equal low bytes in
 // xn, from the high byte an equal high byte in xp and xn == 0 -- so the common case, no
 // match, is decided without a branch per candidate, and each entry is loaded once.
 template <int MODE, typename Sink>
-__device__ __forceinline__ void tokenise(const uint16_t* e, const uint16_t* __restrict__ dup,
-                                         const BlockGeom& g, Sink& sink) {
+__device__ __forceinline__ void tokenise(const uint16_t* e, Sink& sink) {
   using C = Cands<MODE>;
   constexpr int K = C::kN;
-  constexpr bool kHasDup = MODE == IIV_MODE_HGR;     // every DHGR string is distinct
-  const uint16_t* dup_row = dup + ((size_t)g.o << Mode<MODE>::kBits);
   const int begin = threadIdx.x * kPerThread, end = begin + kPerThread;
-  uint32_t xp[K + 1], xn[K + 1];
-  int dp = 0x40000000, dn = 0x40000000;              // the dup distance of entries p, p + 1
-  auto load = [&](int q, uint32_t* x, int& dd) {
-    if (q >= end) {
+  uint32_t xp[K], xn[K];
+  auto load = [&](int q, uint32_t* x) {
 #pragma unroll
-      for (int k = 0; k <= K; ++k) x[k] = kNoMatch;
-      dd = 0x40000000;
-      return;
-    }
-#pragma unroll
-    for (int k = 0; k < K; ++k) x[k] = diff_at(e, q, C::at(k));
-    if (kHasDup) {
-      dd = dup_at(dup_row, g.col0, g.n_mask, q);
-      x[K] = diff_at(e, q, dd);
-    } else {
-      x[K] = kNoMatch;
-    }
+    for (int k = 0; k < K; ++k) x[k] = q < end ? diff_at(e, q, C::at(k)) : kNoMatch;
   };
   int p = begin, s = 0;
-  load(p, xp, dp);
-  load(p + 1, xn, dn);
+  load(p, xp);
+  load(p + 1, xn);
   while (p < end) {
     // which candidates give at least three bytes from here
     uint32_t mask = 0;
 #pragma unroll
-    for (int k = 0; k <= K; ++k) {
+    for (int k = 0; k < K; ++k) {
       const bool ok = s == 0 ? (xp[k] == 0 && (xn[k] & 0xffu) == 0)
                              : ((xp[k] >> 8) == 0 && xn[k] == 0);
       mask |= (uint32_t)ok << k;
     }
-    // a dup match must keep its distance in the next entry
-    if (kHasDup && dn != dp) mask &= ~(1u << K);
     if (mask == 0) {
       const uint32_t v = e[padded(p)];
       sink.lit(s ? v >> 8 : v & 0xffu);
@@ -218,9 +186,8 @@ __device__ __forceinline__ void tokenise(const uint16_t* e, const uint16_t* __re
         s = 0;
         ++p;
 #pragma unroll
-        for (int k = 0; k <= K; ++k) xp[k] = xn[k];
-        dp = dn;
-        load(p + 1, xn, dn);
+        for (int k = 0; k < K; ++k) xp[k] = xn[k];
+        load(p + 1, xn);
       }
       continue;
     }
@@ -230,21 +197,17 @@ __device__ __forceinline__ void tokenise(const uint16_t* e, const uint16_t* __re
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       if (((mask >> k) & 1u) && best < room) {
-        const int len = match_bytes<false>(e, dup_row, g.col0, g.n_mask, p, s, end, C::at(k));
+        const int len = match_bytes(e, p, s, end, C::at(k));
         if (len > best) { best = len; best_d = C::at(k); }
       }
-    }
-    if (kHasDup && ((mask >> K) & 1u) && best < room) {
-      const int len = match_bytes<true>(e, dup_row, g.col0, g.n_mask, p, s, end, dp);
-      if (len > best) { best = len; best_d = dp; }
     }
     sink.match(best, 2 * best_d);
     const int b = 2 * p + s + best;
     p = b >> 1;
     s = b & 1;
     if (p < end) {
-      load(p, xp, dp);
-      load(p + 1, xn, dn);
+      load(p, xp);
+      load(p + 1, xn);
     }
   }
 }
@@ -271,8 +234,7 @@ __device__ __forceinline__ uint32_t gf2_times(const uint32_t* __restrict__ op, u
 
 template <int MODE>
 __global__ void __launch_bounds__(kDThreads)
-deflate_survey_kernel(const uint16_t* __restrict__ table, const uint16_t* __restrict__ dup,
-                      uint32_t* __restrict__ hist, uint32_t* __restrict__ block_crc,
+deflate_survey_kernel(const uint16_t* __restrict__ table, uint32_t* __restrict__ hist, uint32_t* __restrict__ block_crc,
                       const uint32_t* __restrict__ crc_ops, int sample_every) {
   __shared__ __align__(16) uint16_t e[kPaddedEntries];
   __shared__ uint32_t crc_table[256];
@@ -319,7 +281,7 @@ deflate_survey_kernel(const uint16_t* __restrict__ table, const uint16_t* __rest
   if (sample_every > 0 && block % (uint32_t)sample_every == 0) {
     const BlockGeom g = geom<MODE>(block);
     HistSink sink{h};
-    tokenise<MODE>(e, dup, g, sink);
+    tokenise<MODE>(e, sink);
     __syncthreads();
     uint32_t* out = hist + (size_t)g.o * kHist;
     for (int k = t; k < kHist; k += kDThreads)
@@ -374,7 +336,7 @@ struct EmitSink {
 
 template <int MODE>
 __global__ void __launch_bounds__(kDThreads)
-deflate_encode_kernel(const uint16_t* __restrict__ table, const uint16_t* __restrict__ dup,
+deflate_encode_kernel(const uint16_t* __restrict__ table,
                       const uint32_t* __restrict__ codes, uint8_t* __restrict__ scratch,
                       uint32_t* __restrict__ sizes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -392,7 +354,7 @@ deflate_encode_kernel(const uint16_t* __restrict__ table, const uint16_t* __rest
   load_block(table, block, e);
   __syncthreads();
   EmitSink emit{code, tbuf + t, 0ull, 0, 0};
-  tokenise<MODE>(e, dup, g, emit);
+  tokenise<MODE>(e, emit);
   const uint32_t eob = code[256];
   if (t == kDThreads - 1) {
     emit.put(eob & 0xffffu, (int)(eob >> 16));   // end of block
@@ -510,33 +472,32 @@ static int n_blocks_of(int mode) {
   return (int)(((size_t)n_off << (2 * bits)) / kBlockEntries);
 }
 
-extern "C" int iiv_deflate_survey(int mode, const uint16_t* d_table, const uint16_t* d_dup,
-                                  uint32_t* d_hist, uint32_t* d_block_crc,
+extern "C" int iiv_deflate_survey(int mode, const uint16_t* d_table, uint32_t* d_hist, uint32_t* d_block_crc,
                                   const uint32_t* d_crc_ops, int sample_every, void* stream) {
   IIV_REQUIRE(mode == IIV_MODE_HGR || mode == IIV_MODE_DHGR, "bad mode %d", mode);
-  IIV_REQUIRE(d_table && d_dup && d_hist && d_block_crc && d_crc_ops && sample_every >= 0,
+  IIV_REQUIRE(d_table && d_hist && d_block_crc && d_crc_ops && sample_every >= 0,
               "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int n_off = mode == IIV_MODE_HGR ? 2 : 4;
   IIV_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * kHist * n_off, st));
   const int n = n_blocks_of(mode);
   if (mode == IIV_MODE_HGR)
-    deflate_survey_kernel<IIV_MODE_HGR><<<n, kDThreads, 0, st>>>(d_table, d_dup, d_hist,
+    deflate_survey_kernel<IIV_MODE_HGR><<<n, kDThreads, 0, st>>>(d_table, d_hist,
                                                                   d_block_crc, d_crc_ops,
                                                                   sample_every);
   else
-    deflate_survey_kernel<IIV_MODE_DHGR><<<n, kDThreads, 0, st>>>(d_table, d_dup, d_hist,
+    deflate_survey_kernel<IIV_MODE_DHGR><<<n, kDThreads, 0, st>>>(d_table, d_hist,
                                                                    d_block_crc, d_crc_ops,
                                                                    sample_every);
   IIV_LAUNCH_CHECK("deflate_survey_kernel");
   return 0;
 }
 
-extern "C" int iiv_deflate_encode(int mode, const uint16_t* d_table, const uint16_t* d_dup,
+extern "C" int iiv_deflate_encode(int mode, const uint16_t* d_table,
                                   const uint32_t* d_codes, uint8_t* d_scratch,
                                   uint32_t* d_sizes, void* stream) {
   IIV_REQUIRE(mode == IIV_MODE_HGR || mode == IIV_MODE_DHGR, "bad mode %d", mode);
-  IIV_REQUIRE(d_table && d_dup && d_codes && d_scratch && d_sizes, "null pointer");
+  IIV_REQUIRE(d_table && d_codes && d_scratch && d_sizes, "null pointer");
   IIV_REQUIRE(((uintptr_t)d_scratch & 15) == 0, "scratch must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int n = n_blocks_of(mode);
@@ -546,13 +507,13 @@ extern "C" int iiv_deflate_encode(int mode, const uint16_t* d_table, const uint1
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncodeSmem);
     if (e == cudaSuccess)
       deflate_encode_kernel<IIV_MODE_HGR><<<n, kDThreads, kEncodeSmem, st>>>(
-          d_table, d_dup, d_codes, d_scratch, d_sizes);
+          d_table, d_codes, d_scratch, d_sizes);
   } else {
     e = cudaFuncSetAttribute(deflate_encode_kernel<IIV_MODE_DHGR>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncodeSmem);
     if (e == cudaSuccess)
       deflate_encode_kernel<IIV_MODE_DHGR><<<n, kDThreads, kEncodeSmem, st>>>(
-          d_table, d_dup, d_codes, d_scratch, d_sizes);
+          d_table, d_codes, d_scratch, d_sizes);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "deflate_encode_kernel");

@@ -11,11 +11,10 @@ literal/length and distance alphabets (RFC 1951 section 3.2), the dynamic-block 
 announces them, and -- afterwards -- the CRC-32 of the whole member from the CRCs of the
 device's blocks (zlib's ``crc32_combine`` construction).
 
-The device's blocks are ordinary deflate: a dynamic-Huffman block of literals, runs of
-repeated entries (distance 2, i.e. the zeros above and around the diagonal and any other
-repeats) and repeats of an earlier COLUMN with the same pixel string (HGR maps 16 384 masked
-values onto 10 710 strings), followed by an empty stored block that byte-aligns it (the
-pigz construction npz_io.py uses too).  Any inflater reads the result.
+The device's blocks are ordinary deflate: a dynamic-Huffman block of literal bytes and of
+matches at a few fixed distances (runs of repeated entries, i.e. the zeros above the
+diagonal, and repeats of an earlier column), followed by an empty stored block that
+byte-aligns it (the pigz construction npz_io.py uses too).  Any inflater reads the result.
 """
 
 import zlib

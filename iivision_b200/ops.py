@@ -179,33 +179,6 @@ def table_download(mode, table: torch.Tensor, host_ptr: int, row_begin=0, row_en
 _deflate_cache = {}
 
 
-def duplicate_columns(mode) -> torch.Tensor:
-    """uint16[n_off, 2^bits] on the device: for column j, how many entries back the previous
-    column with the same nominal-colour pixel string sits (0 = none).  Columns with equal
-    strings hold equal entries in every row (make_data_tables.py:165-171 computes an entry
-    from the two strings alone), which is what the deflate's column matches rely on."""
-    m = mode_id(mode)
-    key = ("dup", m, torch.cuda.current_device())
-    if key not in _deflate_cache:
-        pix = all_pixel_strings(m).cpu().numpy()        # [n_off, n, dots] uint8
-        n_off, n, dots = pix.shape
-        out = np.zeros((n_off, n), dtype=np.uint16)
-        for o in range(n_off):
-            keys = np.zeros(n, dtype=np.uint64)
-            hi = np.zeros(n, dtype=np.uint64)
-            for t in range(dots):                        # 4 bits per pixel: 72 bits for HGR
-                if t < 16:
-                    keys |= pix[o, :, t].astype(np.uint64) << np.uint64(4 * t)
-                else:
-                    hi |= pix[o, :, t].astype(np.uint64) << np.uint64(4 * (t - 16))
-            order = np.lexsort((np.arange(n), keys, hi))
-            same = (keys[order][1:] == keys[order][:-1]) & (hi[order][1:] == hi[order][:-1])
-            back = order[1:] - order[:-1]                # positive: ties sort by column
-            out[o, order[1:][same]] = back[same]
-        _deflate_cache[key] = torch.from_numpy(out.view(np.int16)).cuda().view(torch.uint16)
-    return _deflate_cache[key]
-
-
 def deflate_table(mode, table: torch.Tensor, sample_every: int = 8, timings: dict = None):
     """Raw-deflate stream of a table resident in HBM (reference layout).  Returns
     (stream uint8 device tensor, block sizes uint32[n_blocks] host, block CRC-32s
@@ -227,7 +200,6 @@ def deflate_table(mode, table: torch.Tensor, sample_every: int = 8, timings: dic
     block_bytes, stride = int(lib.iiv_deflate_block_bytes()), int(lib.iiv_deflate_block_stride())
     n_off = NUM_OFFSETS[m]
     n_blocks = table.numel() * 2 // block_bytes
-    dup = duplicate_columns(m)
     key = ("crc_ops", torch.cuda.current_device())
     if key not in _deflate_cache:
         _deflate_cache[key] = torch.from_numpy(
@@ -236,7 +208,7 @@ def deflate_table(mode, table: torch.Tensor, sample_every: int = 8, timings: dic
     hist = torch.empty((n_off, deflate.HIST_STRIDE), dtype=torch.int32, device="cuda")
     block_crc = torch.empty((n_blocks,), dtype=torch.int32, device="cuda")
     mark("start")
-    check(lib.iiv_deflate_survey(m, _ptr(table), _ptr(dup), _ptr(hist), _ptr(block_crc),
+    check(lib.iiv_deflate_survey(m, _ptr(table), _ptr(hist), _ptr(block_crc),
                                  _ptr(crc_ops), int(sample_every), _stream()))
     mark("survey")
     h = hist.cpu().numpy().view(np.uint32)              # synchronises: the codes need it
@@ -245,7 +217,7 @@ def deflate_table(mode, table: torch.Tensor, sample_every: int = 8, timings: dic
     scratch = torch.empty((n_blocks * stride,), dtype=torch.uint8, device="cuda")
     sizes = torch.empty((n_blocks,), dtype=torch.int32, device="cuda")
     mark("host: huffman codes")
-    check(lib.iiv_deflate_encode(m, _ptr(table), _ptr(dup), _ptr(d_codes), _ptr(scratch),
+    check(lib.iiv_deflate_encode(m, _ptr(table), _ptr(d_codes), _ptr(scratch),
                                  _ptr(sizes), _stream()))
     mark("encode")
     ends = torch.cumsum(sizes.to(torch.int64), 0)       # bookkeeping of 2^15 sizes

@@ -126,26 +126,28 @@ int iiv_table_download(int mode, const uint16_t* d_table, uint16_t* h_table,
  * make_edit_distance writes np.savez_compressed(..., edit_distance=dist)
  * (make_data_tables.py:186-188).  The table (reference layout, resident in HBM) is cut into
  * blocks of iiv_deflate_block_bytes() bytes; each becomes one dynamic-Huffman deflate block
- * (RFC 1951) plus an empty stored block that byte-aligns it.  Matches are runs of repeated
- * entries and repeats of an earlier column with the same pixel string: d_dup
- * uint16[n_offsets][2^bits] = entries back to the previous column with the same string (0 =
- * none).  Three stream-ordered steps, the host builds the Huffman codes in between:
+ * (RFC 1951) plus an empty stored block that byte-aligns it, so the blocks are independent
+ * and their concatenation (+ a final empty block) is one raw-deflate stream.  Matches are
+ * byte runs that repeat the bytes a whole number of entries back, at a few fixed column
+ * distances per mode.  Three stream-ordered steps, the host builds the Huffman codes in
+ * between (iivision_b200/deflate.py):
  *   survey  d_hist uint32[n_offsets][320] (286 literal/length + 30 distance counters, from
  *           every sample_every-th block; zeroed here) and d_block_crc uint32[n_blocks], the
  *           CRC-32 of every block; d_crc_ops uint32[7][32] = GF(2) operators appending
  *           256 << k zero bytes to a CRC (zlib's crc32_combine)
  *   encode  d_codes uint32[n_offsets][413]: reversed code | length << 16 for the 286 + 30
  *           symbols, header bit count, header bits (deflate.CodeTable.words());  d_scratch
- *           n_blocks x iiv_deflate_block_stride() bytes, d_sizes uint32[n_blocks]
+ *           n_blocks x iiv_deflate_block_stride() bytes, 16-byte aligned; d_sizes
+ *           uint32[n_blocks]: compressed bytes of each block (a block that would not shrink
+ *           is stored)
  *   gather  packs the blocks back to back: block b to d_out + d_offsets[b] */
 size_t iiv_deflate_block_bytes(void);
 size_t iiv_deflate_block_stride(void);
-int iiv_deflate_survey(int mode, const uint16_t* d_table, const uint16_t* d_dup,
-                       uint32_t* d_hist, uint32_t* d_block_crc, const uint32_t* d_crc_ops,
-                       int sample_every, void* stream);
-int iiv_deflate_encode(int mode, const uint16_t* d_table, const uint16_t* d_dup,
-                       const uint32_t* d_codes, uint8_t* d_scratch, uint32_t* d_sizes,
+int iiv_deflate_survey(int mode, const uint16_t* d_table, uint32_t* d_hist,
+                       uint32_t* d_block_crc, const uint32_t* d_crc_ops, int sample_every,
                        void* stream);
+int iiv_deflate_encode(int mode, const uint16_t* d_table, const uint32_t* d_codes,
+                       uint8_t* d_scratch, uint32_t* d_sizes, void* stream);
 int iiv_deflate_gather(const uint8_t* d_scratch, const uint32_t* d_sizes,
                        const int64_t* d_offsets, int n_blocks, uint8_t* d_out, void* stream);
 

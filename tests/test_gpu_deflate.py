@@ -48,25 +48,6 @@ def test_deflate_round_trip(ops, oracle_luts, mode, pid, layout):
     assert ours < (1.3 if layout == 0 else 1.45) * theirs
 
 
-def test_duplicate_columns_are_duplicates(ops):
-    """d_dup really points at an earlier column with the same pixel string, and at the
-    nearest one."""
-    for mode in ("HGR", "DHGR"):
-        pix = ops.all_pixel_strings(mode).cpu().numpy()
-        dup = ops.duplicate_columns(mode).cpu().numpy().view(np.uint16)
-        for o in range(pix.shape[0]):
-            cols = np.flatnonzero(dup[o])
-            if mode == "DHGR":
-                assert cols.size == 0            # all 8192 strings are distinct
-                continue
-            assert cols.size == 16384 - len(np.unique(pix[o], axis=0))
-            back = cols - dup[o][cols].astype(np.int64)
-            assert (back >= 0).all() and np.array_equal(pix[o][cols], pix[o][back])
-            for j in cols[::97]:
-                between = pix[o][j - int(dup[o][j]) + 1:j]
-                assert not (between == pix[o][j]).all(axis=1).any()
-
-
 def test_make_edit_distance_file_is_a_plain_npz(ops, oracle_luts, tmp_path, monkeypatch):
     from iivision_b200 import colours, make_data_tables as mdt, npz_io, palette, screen
     from oracle import tables
