@@ -30,7 +30,7 @@ def _flat_frames(mode, n_frames, rng):
     return out
 
 
-@pytest.mark.parametrize("case", range(int(__import__("os").environ.get("IIV_RANDOM_CASES", "10"))))
+@pytest.mark.parametrize("case", range(int(__import__("os").environ.get("IIV_RANDOM_CASES", "120"))))
 def test_random_configurations(oracle_tables, device_tables, case):
     from iivision_b200 import ops
     from iivision_b200.synth import synthetic_frames
