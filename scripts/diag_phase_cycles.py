@@ -3,7 +3,7 @@ sys.path.insert(0,'.')
 from iivision_b200 import ops, synth, palette
 lut = ops.lut_cie2000(palette.NTSCPalette.rgb_by_value())
 table = ops.table_generate("DHGR", lut, layout=ops.LAYOUT_SYMMETRIC)
-n_frames=4
+n_frames=int(sys.argv[1]) if len(sys.argv) > 1 else 4
 clips = synth.synthetic_frames("DHGR", n_frames, 1.0, seed=100)[None]
 segs = synth.movie_schedule("DHGR", n_frames)
 tmem = torch.from_numpy(np.ascontiguousarray(clips)).cuda()
