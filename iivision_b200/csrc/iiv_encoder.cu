@@ -476,6 +476,11 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         state + (is_aux ? kOffPrioAux : kOffPrioMain));
     uint8_t* g_mem = state + (is_aux ? kOffAux : kOffMain);
 
+#ifdef IIV_X_TIMING
+    __shared__ long long pa_sh[8];
+    long long pa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pa_prev = clock64();
+#endif
     // ======================= phase A: score + heapify ===========================
     // thread t owns cells [32t, 32t+32): page t>>3, offsets (t&7)*32 .. +31.
     const int cell0 = t * 32;
@@ -542,6 +547,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     if (lane == 31) sm.scan[warp] = incl;
     if (lane == 0) sm.wmin64[warp] = (uint64_t)prio_sum;
     __syncthreads();
+#ifdef IIV_X_TIMING
+    if (t == 0) { const long long tn = clock64(); pa[1] = tn - pa_prev; pa_prev = tn; }
+#endif
     int rank0 = incl - nz;
     int n_heap = 0;
     int64_t prio_total = 0;
@@ -582,6 +590,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       np_ready = 0;
     }
     __syncthreads();
+#ifdef IIV_X_TIMING
+    if (t == 0) { const long long tn = clock64(); pa[2] = tn - pa_prev; pa_prev = tn; }
+#endif
     {
       int r = rank0;
 #pragma unroll
@@ -593,6 +604,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       }
     }
     __syncthreads();
+#ifdef IIV_X_TIMING
+    if (t == 0) { const long long tn = clock64(); pa[3] = tn - pa_prev; pa_prev = tn; }
+#endif
     if (n_heap > 0) pos_np = pos_np + n_heap - 624 * twists;
     // Only a prefix of the heap can ever be popped in this segment: every opcode
     // pops one live entry and can zero at most two others (video.py:170), so no more
@@ -716,6 +730,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     while (P < n_sorted) P <<= 1;
     for (int k = n_sorted + t; k < P; k += kThreads) sm.keys[k] = kDead;
     __syncthreads();
+#ifdef IIV_X_TIMING
+    if (t == 0) { const long long tn = clock64(); pa[4] = tn - pa_prev; pa_prev = tn; }
+#endif
     // Bitonic network.  Steps whose partner distance is below 64 never leave a 64-key
     // chunk, so a warp runs all of them back to back on a chunk held in registers (two
     // keys per lane, shuffles for distances < 32); only the wider steps go through
@@ -738,6 +755,10 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       }
       for (int c = warp; c < P / 64; c += kWarps) sort_chunk64(sm.keys + 64 * c, 64 * c, lane, k, k);
       __syncthreads();
+#ifdef IIV_X_TIMING
+    if (t == 0) { const long long tn = clock64(); pa[5] = tn - pa_prev; pa_prev = tn; }
+    if (t == 0) for (int k = 0; k < 8; ++k) pa_sh[k] = pa[k];
+#endif
     }
     const int n_first = n_sorted;   // entries of the sorted array phase B may walk
 
@@ -1133,6 +1154,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         IIV_T(6)
       }
 #ifdef IIV_X_TIMING
+      if (lane == 0 && clip == 0)
+        printf("seg %d phaseA: score+fold %lld nonces %lld keys %lld select %lld sort %lld\n", seg, pa_sh[1], pa_sh[2], pa_sh[3], pa_sh[4], pa_sh[5]);
       if (lane == 0 && clip == 0)
         printf("seg %d emitted %d | top %lld recwait %lld classify %lld digest %lld winners %lld stores %lld sync %lld | settled %d cont %d redigest %d\n",
                seg, emitted, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6],
