@@ -38,61 +38,72 @@ IntOrArray = Union[np.uint64, np.ndarray]
 
 
 def y_to_base_addr(y: int, page: int = 0) -> int:
-    """Maps y coordinate to base address on given screen page."""
-    third, rest = divmod(y, 64)
-    eighth, line = divmod(rest, 8)
-    return 8192 * (page + 1) + 1024 * line + 128 * eighth + 40 * third
+    """Maps y coordinate to base address on given screen page.
+
+    The hi-res interleave: the 8 lines of a character row sit 1 KiB apart, the 8 character
+    rows of a third of the screen 128 bytes apart, the three thirds 40 bytes apart (which
+    is what leaves 8 unused bytes behind every third row: the screen holes)."""
+    line, row, third = y & 7, (y >> 3) & 7, y >> 6
+    return ((page + 1) << 13) + (line << 10) + (row << 7) + 40 * third
 
 
 Y_TO_BASE_ADDR = [[y_to_base_addr(y, p) for y in range(192)] for p in (0, 1)]
 
-PAGE_OFFSET_TO_X = np.zeros((32, 256), dtype=np.uint8)
-PAGE_OFFSET_TO_Y = np.zeros((32, 256), dtype=np.uint8)
-X_Y_TO_PAGE = np.zeros((192, 40), dtype=np.uint8)
-X_Y_TO_OFFSET = np.zeros((192, 40), dtype=np.uint8)
-SCREEN_HOLES = np.full((32, 256), True, dtype=np.bool_)
-ADDR_TO_COORDS = {}
+
+def _address_tables():
+    """The (y, x) <-> (page, offset) tables of reference screen.py:26-69, built from the
+    address of every visible byte of page 1 at once."""
+    addr = np.asarray(Y_TO_BASE_ADDR[0])[:, None] + np.arange(40)[None, :]      # [192][40]
+    page, offset = (addr >> 8) - 32, addr & 255
+    ys, xs = np.broadcast_arrays(np.arange(192)[:, None], np.arange(40)[None, :])
+    to_x = np.zeros((32, 256), dtype=np.uint8)
+    to_y = np.zeros((32, 256), dtype=np.uint8)
+    holes = np.ones((32, 256), dtype=np.bool_)
+    to_x[page, offset] = xs
+    to_y[page, offset] = ys
+    holes[page, offset] = False
+    coords = {}
+    for p in (0, 1):
+        base = np.asarray(Y_TO_BASE_ADDR[p])[:, None] + np.arange(40)[None, :]
+        coords.update({int(a): (p, int(y), int(x))
+                       for a, y, x in zip(base.ravel(), ys.ravel(), xs.ravel())})
+    return to_x, to_y, page.astype(np.uint8), offset.astype(np.uint8), holes, coords
 
 
-def _populate_mappings():
-    for y in range(192):
-        base = Y_TO_BASE_ADDR[0][y]
-        page, first = divmod(base, 256)
-        for x in range(40):
-            PAGE_OFFSET_TO_Y[page - 32, first + x] = y
-            PAGE_OFFSET_TO_X[page - 32, first + x] = x
-            X_Y_TO_PAGE[y, x] = page - 32
-            X_Y_TO_OFFSET[y, x] = first + x
-            SCREEN_HOLES[page - 32, first + x] = False
-            for p in range(2):
-                ADDR_TO_COORDS[Y_TO_BASE_ADDR[p][y] + x] = (p, y, x)
+(PAGE_OFFSET_TO_X, PAGE_OFFSET_TO_Y, X_Y_TO_PAGE, X_Y_TO_OFFSET, SCREEN_HOLES,
+ ADDR_TO_COORDS) = _address_tables()
 
 
-_populate_mappings()
+def _checked_screen_page(screen_page: int) -> int:
+    if screen_page not in (1, 2):
+        raise ValueError("Screen page out of bounds: %d" % screen_page)
+    return screen_page
+
+
+def _bytes_or_zeros(data, shape) -> np.ndarray:
+    """The caller's array (adopted, not copied, as the reference does) or a blank screen."""
+    if data is None:
+        return np.zeros(shape, dtype=np.uint8)
+    if data.shape != shape:
+        raise ValueError("Unexpected shape: %r" % (data.shape,))
+    return data
 
 
 class FlatMemoryMap:
     """Linear 8K representation of HGR screen memory."""
 
     def __init__(self, screen_page: int, data: np.array = None):
-        if screen_page not in [1, 2]:
-            raise ValueError("Screen page out of bounds: %d" % screen_page)
-        self.screen_page = screen_page
+        self.screen_page = _checked_screen_page(screen_page)
         self._addr_start = 8192 * self.screen_page
         self._addr_end = self._addr_start + 8191
-        if data is not None:
-            if data.shape != (8192,):
-                raise ValueError("Unexpected shape: %r" % (data.shape,))
-            self.data = data
-        else:
-            self.data = np.zeros((8192,), dtype=np.uint8)
+        self.data = _bytes_or_zeros(data, (8192,))
 
     def to_memory_map(self):
         return MemoryMap(self.screen_page, self.data.reshape((32, 256)))
 
     def write(self, addr: int, val: int) -> None:
         """Updates screen image to set 0xaddr = val (including screen holes)"""
-        if addr < self._addr_start or addr > self._addr_end:
+        if not self._addr_start <= addr <= self._addr_end:
             raise ValueError("Address out of range: 0x%04x" % addr)
         self.data[addr - self._addr_start] = val
 
@@ -101,16 +112,9 @@ class MemoryMap:
     """Page/offset-structured representation of HGR screen memory."""
 
     def __init__(self, screen_page: int, page_offset: np.array = None):
-        if screen_page not in [1, 2]:
-            raise ValueError("Screen page out of bounds: %d" % screen_page)
-        self.screen_page = screen_page
+        self.screen_page = _checked_screen_page(screen_page)
         self._page_start = 32 * screen_page
-        if page_offset is not None:
-            if page_offset.shape != (32, 256):
-                raise ValueError("Unexpected shape: %r" % (page_offset.shape,))
-            self.page_offset = page_offset
-        else:
-            self.page_offset = np.zeros((32, 256), dtype=np.uint8)
+        self.page_offset = _bytes_or_zeros(page_offset, (32, 256))
 
     def to_flat_memory_map(self) -> FlatMemoryMap:
         return FlatMemoryMap(self.screen_page, self.page_offset.reshape(8192))
