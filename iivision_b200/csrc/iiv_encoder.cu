@@ -482,83 +482,99 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     long long pa_prev = clock64();
 #endif
     // ======================= phase A: score + heapify ===========================
-    // thread t owns cells [32t, 32t+32): page t>>3, offsets (t&7)*32 .. +31.
-    const int cell0 = t * 32;
-    const int page_a = t >> 3;
-    const int colbase = page_a * 128 + (t & 7) * 16;
-    // All loads of a stage are issued before anything waits on them: 8 x 16-byte target
-    // words and priorities first, then the 32 table gathers.
+    // thread t owns offset t of every page: cells 256 k + t, k = 0..31.  Lanes thus hold
+    // consecutive cells, so every shared-memory access below -- source words, priorities,
+    // diff weights, keys -- is to consecutive addresses (32 consecutive cells per thread
+    // would put all 32 lanes on one bank: the fold and the key build then cost more than the
+    // gathers), and the global loads of target words and priorities are coalesced.
+    // All loads of a stage are issued before anything waits on them: the target words
+    // first, then the 32 table gathers.
+    const int half_a = t & 1;
+    const int o_a = byte_offset<MODE>(half_a, is_aux);
     uint32_t dwv[32];
     {
-      ulonglong2 g2[8];
+      uint64_t g[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        g2[c] = __ldg(reinterpret_cast<const ulonglong2*>(tp + colbase) + c);
+      for (int k = 0; k < 32; ++k) g[k] = __ldg(tp + 128 * k + (t >> 1));
       uint32_t gidx[32];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const uint64_t s = sm.src[colbase + c];
-        const uint64_t g = (c & 1) ? g2[c >> 1].y : g2[c >> 1].x;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int o = byte_offset<MODE>(half, is_aux);
-          const uint32_t x = mask_shift<MODE>(s, o), y = mask_shift<MODE>(g, o);
-          gidx[2 * c + half] = ((uint32_t)o << (2 * M::kBits)) + (x << M::kBits) + y;
-        }
+      for (int k = 0; k < 32; ++k) {
+        const uint64_t s = sm.src[128 * k + (t >> 1)];
+        const uint32_t x = mask_shift<MODE>(s, o_a), y = mask_shift<MODE>(g[k], o_a);
+        gidx[k] = ((uint32_t)o_a << (2 * M::kBits)) + (x << M::kBits) + y;
       }
 #pragma unroll
       for (int k = 0; k < 32; ++k) dwv[k] = ldg_table(table + gidx[k]);
+      if (is_hole(t)) {                              // video.py:111 (offset t of any page)
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (is_hole((t & 7) * 32 + k)) dwv[k] = 0;   // video.py:111
+        for (int k = 0; k < 32; ++k) dwv[k] = 0;
+      }
     }
     int64_t prio_sum = 0;
-    int nz = 0;
     uint32_t nzmask = 0;
     {
-      int4 pv[8];
+      int32_t pv[32];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) pv[q] = reinterpret_cast<const int4*>(g_prio + cell0)[q];
+      for (int k = 0; k < 32; ++k) pv[k] = g_prio[256 * k + t];
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        const int4 v = pv[k >> 2];
-        int32_t p = (k & 3) == 0 ? v.x : (k & 3) == 1 ? v.y : (k & 3) == 2 ? v.z : v.w;
+        int32_t p = pv[k];
         prio_sum += p;
         if (dwv[k] == 0) p = 0;          // video.py:115
         p += (int32_t)dwv[k];            // video.py:116
-        sm.prio[cell0 + k] = p;
-        sm.dw[cell0 + k] = (uint16_t)dwv[k];
-        if (p != 0) {
-          ++nz;
-          nzmask |= 1u << k;
-        }
+        sm.prio[256 * k + t] = p;
+        sm.dw[256 * k + t] = (uint16_t)dwv[k];
+        if (p != 0) nzmask |= 1u << k;
       }
     }
-    // block-wide sums: exclusive scan of nz, total of prio_sum.
-    int incl = nz;
+    // Row-major rank of every nonzero cell (its draw from stream N, video.py:259-267): page k
+    // of warp w holds cells 256 k + 32 w .. + 31, so the counts are scanned in (k, w) order.
+    uint32_t* cnt = &sm.hist[0][0];      // [32 pages][8 warps]; the select's scratch, idle now
+    static_assert(sizeof(sm.hist) >= 32 * (kThreads / 32) * 4 + 4, "rank scratch too small");
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
+    for (int k = 0; k < 32; ++k) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, (nzmask >> k) & 1u);
+      if (lane == k) cnt[k * (kThreads / 32) + warp] = (uint32_t)__popc(bal);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1)
       prio_sum += __shfl_xor_sync(0xffffffffu, prio_sum, d);
-    if (lane == 31) sm.scan[warp] = incl;
     if (lane == 0) sm.wmin64[warp] = (uint64_t)prio_sum;
+    __syncthreads();
+    if (warp == 0) {
+      // exclusive scan of the 256 counts: lane l owns entries 8 l .. 8 l + 7 (page l)
+      uint32_t c[8], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        c[q] = cnt[8 * lane + q];
+        tot += c[q];
+      }
+      uint32_t incl = tot;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      uint32_t run = incl - tot;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        cnt[8 * lane + q] = run;
+        run += c[q];
+      }
+      if (lane == 31) cnt[256] = incl;         // n_heap
+    }
     __syncthreads();
 #ifdef IIV_X_TIMING
     if (t == 0) { const long long tn = clock64(); pa[1] = tn - pa_prev; pa_prev = tn; }
 #endif
-    int rank0 = incl - nz;
-    int n_heap = 0;
+    const int n_heap = (int)cnt[256];
     int64_t prio_total = 0;
 #pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-      if (w < warp) rank0 += sm.scan[w];
-      n_heap += sm.scan[w];
-      prio_total += (int64_t)sm.wmin64[w];
-    }
+    for (int w = 0; w < kThreads / 32; ++w) prio_total += (int64_t)sm.wmin64[w];
+    // this thread's rank bases, before the scratch is reused: base of (page k, this warp)
+    uint32_t rank_base[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) rank_base[k] = cnt[k * (kThreads / 32) + warp];
     // stream N draws: the k-th nonzero cell (row-major) takes the low byte of word
     // pos_np + k (video.py:259-267).  Blocks of 624 words are generated one after the
     // other (each needs its predecessor); their bytes land in a per-draw array that
@@ -593,14 +609,12 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
 #ifdef IIV_X_TIMING
     if (t == 0) { const long long tn = clock64(); pa[2] = tn - pa_prev; pa_prev = tn; }
 #endif
-    {
-      int r = rank0;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        if (nzmask & (1u << k)) {
-          sm.keys[r] = first_pass_key(sm.prio[cell0 + k], np_nonce[r], cell0 + k);
-          ++r;
-        }
+    for (int k = 0; k < 32; ++k) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, (nzmask >> k) & 1u);
+      if ((nzmask >> k) & 1u) {
+        const int r = (int)rank_base[k] + __popc(bal & ((1u << lane) - 1u));
+        sm.keys[r] = first_pass_key(sm.prio[256 * k + t], np_nonce[r], 256 * k + t);
       }
     }
     __syncthreads();
