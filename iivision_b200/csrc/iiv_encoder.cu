@@ -501,15 +501,26 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       for (int k = 0; k < 32; ++k) {
         const uint64_t s = sm.src[128 * k + (t >> 1)];
         const uint32_t x = mask_shift<MODE>(s, o_a), y = mask_shift<MODE>(g[k], o_a);
-        gidx[k] = ((uint32_t)o_a << (2 * M::kBits)) + (x << M::kBits) + y;
+        // a window that already shows what the target shows is at distance 0 (the tables'
+        // diagonal): no gather -- on real footage most of the screen; holes likewise
+        // (video.py:111: offset t of any page)
+        gidx[k] = (x == y || is_hole(t))
+                      ? 0xffffffffu
+                      : ((uint32_t)o_a << (2 * M::kBits)) + (x << M::kBits) + y;
       }
 #pragma unroll
-      for (int k = 0; k < 32; ++k) dwv[k] = ldg_table(table + gidx[k]);
-      if (is_hole(t)) {                              // video.py:111 (offset t of any page)
-#pragma unroll
-        for (int k = 0; k < 32; ++k) dwv[k] = 0;
-      }
+      for (int k = 0; k < 32; ++k)
+        dwv[k] = gidx[k] == 0xffffffffu ? 0u : ldg_table(table + gidx[k]);
     }
+#ifdef IIV_X_TIMING
+    {
+      uint32_t chk = 0;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) chk += dwv[k];
+      if (__syncthreads_or(chk == 0xfffffff0u)) pa[7] = 1;
+      if (t == 0) { const long long tn = clock64(); pa[6] = tn - pa_prev; pa_prev = tn; }
+    }
+#endif
     int64_t prio_sum = 0;
     uint32_t nzmask = 0;
     {
@@ -769,11 +780,11 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       }
       for (int c = warp; c < P / 64; c += kWarps) sort_chunk64(sm.keys + 64 * c, 64 * c, lane, k, k);
       __syncthreads();
+    }
 #ifdef IIV_X_TIMING
     if (t == 0) { const long long tn = clock64(); pa[5] = tn - pa_prev; pa_prev = tn; }
     if (t == 0) for (int k = 0; k < 8; ++k) pa_sh[k] = pa[k];
 #endif
-    }
     const int n_first = n_sorted;   // entries of the sorted array phase B may walk
 
     // ======================= phase B: emit opcodes ==============================
@@ -1169,7 +1180,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       }
 #ifdef IIV_X_TIMING
       if (lane == 0 && clip == 0)
-        printf("seg %d phaseA: score+fold %lld nonces %lld keys %lld select %lld sort %lld\n", seg, pa_sh[1], pa_sh[2], pa_sh[3], pa_sh[4], pa_sh[5]);
+        printf("seg %d phaseA: gathers %lld fold+rank %lld nonces %lld keys %lld select %lld sort %lld\n", seg, pa_sh[6], pa_sh[1], pa_sh[2], pa_sh[3], pa_sh[4], pa_sh[5]);
       if (lane == 0 && clip == 0)
         printf("seg %d emitted %d | top %lld recwait %lld classify %lld digest %lld winners %lld stores %lld sync %lld | settled %d cont %d redigest %d\n",
                seg, emitted, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6],
