@@ -523,6 +523,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
 #endif
     int64_t prio_sum = 0;
     uint32_t nzmask = 0;
+    int32_t p_hi = 0, p_lo = 0x7fffffff;      // extremes of the nonzero priorities
     {
       int32_t pv[32];
 #pragma unroll
@@ -535,7 +536,11 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         p += (int32_t)dwv[k];            // video.py:116
         sm.prio[256 * k + t] = p;
         sm.dw[256 * k + t] = (uint16_t)dwv[k];
-        if (p != 0) nzmask |= 1u << k;
+        if (p != 0) {
+          nzmask |= 1u << k;
+          p_hi = max(p_hi, p);
+          p_lo = min(p_lo, p);
+        }
       }
     }
     // Row-major rank of every nonzero cell (its draw from stream N, video.py:259-267): page k
@@ -550,7 +555,13 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1)
       prio_sum += __shfl_xor_sync(0xffffffffu, prio_sum, d);
-    if (lane == 0) sm.wmin64[warp] = (uint64_t)prio_sum;
+    p_hi = __reduce_max_sync(0xffffffffu, p_hi);
+    p_lo = __reduce_min_sync(0xffffffffu, p_lo);
+    if (lane == 0) {
+      sm.wmin64[warp] = (uint64_t)prio_sum;
+      cnt[264 + warp] = (uint32_t)p_hi;
+      cnt[272 + warp] = (uint32_t)p_lo;
+    }
     __syncthreads();
     if (warp == 0) {
       // exclusive scan of the 256 counts: lane l owns entries 8 l .. 8 l + 7 (page l)
@@ -586,6 +597,19 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     uint32_t rank_base[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) rank_base[k] = cnt[k * (kThreads / 32) + warp];
+    // The select below counts the keys by one 8-bit digit at a time, from the highest bit in
+    // which any two keys can differ: the keys of the largest and the smallest priority bound
+    // them all, so that bit is known before a key exists and the first count is taken while
+    // the keys are being built.
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      p_hi = max(p_hi, (int32_t)cnt[264 + w]);
+      p_lo = min(p_lo, (int32_t)cnt[272 + w]);
+    }
+    const uint64_t key_span = first_pass_key(p_hi, 0u, 0) ^ first_pass_key(p_lo, 0xffu, kCells - 1);
+    const int top_shift = max(0, 63 - __clzll((long long)key_span) - 7);
+    __syncthreads();       // everybody has read the scratch: it becomes the histograms
+    for (int k = t; k < (kThreads / 32) * 257; k += kThreads) (&sm.hist[0][0])[k] = 0;
     // stream N draws: the k-th nonzero cell (row-major) takes the low byte of word
     // pos_np + k (video.py:259-267).  Blocks of 624 words are generated one after the
     // other (each needs its predecessor); their bytes land in a per-draw array that
@@ -625,7 +649,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       const uint32_t bal = __ballot_sync(0xffffffffu, (nzmask >> k) & 1u);
       if ((nzmask >> k) & 1u) {
         const int r = (int)rank_base[k] + __popc(bal & ((1u << lane) - 1u));
-        sm.keys[r] = first_pass_key(sm.prio[256 * k + t], np_nonce[r], 256 * k + t);
+        const uint64_t key = first_pass_key(sm.prio[256 * k + t], np_nonce[r], 256 * k + t);
+        sm.keys[r] = key;
+        atomicAdd(&sm.hist[warp][(uint32_t)(key >> top_shift) & 255u], 1u);
       }
     }
     __syncthreads();
@@ -641,23 +667,9 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     {
       const int need = min(n_heap, 3 * budget);
       if (need < n_heap && need <= kPushedCap && n_heap > 1024) {
-        // digits above the highest bit in which any two keys differ are common to all
-        uint64_t diff = 0;
-        {
-          const uint64_t k0 = sm.keys[0];
-          for (int k = t; k < n_heap; k += kThreads) diff |= sm.keys[k] ^ k0;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, d);
-          if (lane == 0) sm.wmin64[warp] = diff;
-        }
-        __syncthreads();
-        diff = 0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) diff |= sm.wmin64[w];
-        // first digit = the eight bits ending at the highest differing one, so that its
-        // 256 buckets are all in use and the boundary bucket is small: one counting pass
-        // usually settles the selection
-        const int top_shift = diff ? max(0, 63 - __clzll((long long)diff) - 7) : 0;
+        // (first digit = the eight bits ending at the highest bit the keys can differ in, so
+        // that its 256 buckets are in use and the boundary bucket is small: the count taken
+        // during the key build usually settles the selection)
         // The sort pads to a power of two anyway, so the select may stop as soon as the
         // whole bucket holding the need-th key fits in that padding: `need` keys are still
         // guaranteed, a few more ride along for free.
@@ -673,18 +685,24 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         __syncthreads();
         // bits >= fixed of the prefix are settled; a digit may overlap them on the last
         // pass (shift clamped to 0), where its upper bits are then equal for every match
+        bool counted = true;      // the first digit's histogram was taken with the keys
         for (int shift = top_shift, fixed = top_shift + 8; !sm.sel_done;
              fixed = shift, shift = max(shift - 8, 0)) {
-          for (int k = t; k < (kThreads / 32) * 257; k += kThreads) (&sm.hist[0][0])[k] = 0;
-          __syncthreads();
+          if (!counted) {
+            for (int k = t; k < (kThreads / 32) * 257; k += kThreads) (&sm.hist[0][0])[k] = 0;
+            __syncthreads();
+          }
           const uint64_t prefix = sm.sel_prefix;
           const int remaining = sm.sel_remaining;
-          for (int k = t; k < n_heap; k += kThreads) {
-            const uint64_t key = sm.keys[k];
-            if (((key ^ prefix) >> fixed) == 0)
-              atomicAdd(&sm.hist[warp][(uint32_t)(key >> shift) & 255u], 1u);
+          if (!counted) {
+            for (int k = t; k < n_heap; k += kThreads) {
+              const uint64_t key = sm.keys[k];
+              if (((key ^ prefix) >> fixed) == 0)
+                atomicAdd(&sm.hist[warp][(uint32_t)(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
           }
-          __syncthreads();
+          counted = false;
           if (warp == 0) {
             // lane l owns digits 8l .. 8l+7
             uint32_t c[8], tot = 0;
