@@ -512,6 +512,20 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       for (int k = 0; k < 32; ++k)
         dwv[k] = gidx[k] == 0xffffffffu ? 0u : ldg_table(table + gidx[k]);
     }
+    // While the gathers are in flight: the draws of stream N that are already at hand -- the
+    // current block and the successors the twister prepared during the last opcode loop --
+    // go to the per-draw array (more of them than this heapify may need; which is known
+    // only once the gathers are back).  The array borrows the row ring, idle until phase B.
+    uint8_t* np_nonce = reinterpret_cast<uint8_t*>(&sm.ring_row[0][0]);
+    static_assert(sizeof(sm.ring_row) >= kCells, "nonce scratch too small");
+    const int np_early = min(np_ready, kNpPreMax);
+    for (int b = 0; b <= np_early; ++b) {
+      const uint32_t* blk = b == 0 ? sm.mt_np[np_cur] : np_pre_blocks + (b - 1) * 624;
+      for (int k = t; k < 624; k += kThreads) {
+        const int g = b * 624 + k - pos_np;
+        if (g >= 0 && g < kCells) np_nonce[g] = (uint8_t)(mt_temper(blk[k]) & 0xffu);
+      }
+    }
 #ifdef IIV_X_TIMING
     {
       uint32_t chk = 0;
@@ -612,10 +626,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     for (int k = t; k < (kThreads / 32) * 257; k += kThreads) (&sm.hist[0][0])[k] = 0;
     // stream N draws: the k-th nonzero cell (row-major) takes the low byte of word
     // pos_np + k (video.py:259-267).  Blocks of 624 words are generated one after the
-    // other (each needs its predecessor); their bytes land in a per-draw array that
-    // borrows the row ring, idle until phase B.
-    uint8_t* np_nonce = reinterpret_cast<uint8_t*>(&sm.ring_row[0][0]);
-    static_assert(sizeof(sm.ring_row) >= kCells, "nonce scratch too small");
+    // other (each needs its predecessor); the bytes of the blocks that were at hand are in
+    // the per-draw array already (above).
     const int twists = n_heap > 0 ? (pos_np + n_heap - 1) / 624 : 0;
     {
       const uint32_t* blk = sm.mt_np[np_cur];
@@ -629,10 +641,11 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
             blk = sm.mt_np[np_cur];
           }
         }
-        for (int k = t; k < 624; k += kThreads) {
-          const int g = b * 624 + k - pos_np;
-          if (g >= 0 && g < n_heap) np_nonce[g] = (uint8_t)(mt_temper(blk[k]) & 0xffu);
-        }
+        if (b > np_early)
+          for (int k = t; k < 624; k += kThreads) {
+            const int g = b * 624 + k - pos_np;
+            if (g >= 0 && g < n_heap) np_nonce[g] = (uint8_t)(mt_temper(blk[k]) & 0xffu);
+          }
       }
       // the block the position ends in becomes the resident state (before the keys below
       // overwrite the prepared blocks)
