@@ -836,20 +836,21 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     //       (only stores to that page change what was read); then the warp re-digests
     //       the entry itself.  It draws the nonces, picks the two best offsets, updates
     //       priorities, re-queues, publishes the opcode: shared memory + shuffles only.
-    //   applier (warp 4)  commits the stores of every published opcode to the source
-    //       bitmap and memory map (Bitmap.apply), in order.  Nothing in phase B reads
-    //       the source, so this is off the chain.
-    //   twister (warp 3)  prepares the next MT19937 block of stream P in the background and,
-    //       when idle, the next segment's stream N blocks and L2 lines (see below).
+    //   helper (warp 3)  two background jobs: it commits the stores of every published
+    //       opcode to the source bitmap and memory map (Bitmap.apply), in order -- nothing
+    //       in phase B reads the source, so this is off the chain -- and it prepares the
+    //       next MT19937 block of stream P when asked and, when idle, the next segment's
+    //       stream N blocks.  (One warp instead of two: a polling warp costs its
+    //       scheduler's other warps issue slots -- 148 clips +9 %, a single clip +2 %.)
     // A cell whose priority is already 0 is skipped by everyone alike: priorities only
     // ever fall to 0 inside a segment (video.py:140, :159-170).
     // The issue arbiter favours the highest warp id of a scheduler and a spinning warp
     // is nearly always eligible, hence the decision warp is 7 and shares its scheduler
-    // (warp id % 4) with the twister, which is idle or streaming through a block most of
+    // (warp id % 4) with the helper, which is idle or streaming through a block most of
     // the time (swapping it with a producer measured the same); helper loops back off
-    // with nanosleep.
+    // with nanosleep.  Warp 4 has no role in phase B.
     constexpr uint32_t kFull = 0xffffffffu;
-    constexpr int kDecideWarp = 7, kTwistWarp = 3, kApplyWarp = 4;
+    constexpr int kDecideWarp = 7, kHelpWarp = 3;
     constexpr uint32_t kKindLive = 0u, kKindDead = 1u, kKindEndOfHeap = 2u;
     if (t < kRing) {
       sm.ring_tag[t] = 0xffffffffu;
@@ -1445,14 +1446,41 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         }
         __syncwarp();
       }
-    } else if (warp == kApplyWarp) {
-      // applier: Bitmap.apply for (off, o1, o2) of each published record.  Stores only
-      // interact inside a page (a packed word and its two neighbours), so lane i takes
-      // the i-th pending record and records of different pages are applied at once;
-      // records that share a page go in emission order, one per round.  Re-applying an
-      // offset that repeats offsets[0] is idempotent.
-      int applied = 0;
+    } else if (warp == kHelpWarp) {
+      // helper: two background jobs in one warp.
+      //  * twister: prepares the next MT19937 block of stream P when the decision warp asks
+      //    for it and, in idle time, the stream N blocks the next heapify will draw from
+      //    (one nonce per nonzero priority, video.py:259-267: 13 blocks for a full screen);
+      //  * applier: Bitmap.apply for (off, o1, o2) of each published record.  Stores only
+      //    interact inside a page (a packed word and its two neighbours), so lane i takes
+      //    the i-th pending record and records of different pages are applied at once;
+      //    records that share a page go in emission order, one per round.  Re-applying an
+      //    offset that repeats offsets[0] is idempotent.  Nothing in phase B reads the
+      //    source, and the queue is 64 records deep: a block twist in between is no matter.
+      int done = 0, applied = 0;
+      const int np_goal = (seg + 1 < n_segments && P <= kCells / 2) ? kNpPreMax : 0;
+      int np_made = 0;
       while (true) {
+        int req = 0, st = 0, fin = 0;
+        if (lane == 0) {
+          req = (int)ld_acq_u32(&sm.mt_req);    // acquire: the slot to overwrite has been read
+          st = (int)ld_acq_u32(&sm.stop);       // stop is set last, with a release
+          fin = (int)ld_rlx_u32(&sm.final_emitted);
+        }
+        req = __shfl_sync(kFull, req, 0);
+        st = __shfl_sync(kFull, st, 0);
+        fin = __shfl_sync(kFull, fin, 0);
+        if (req > done) {
+          // request n (from 1) replaces the block n behind the segment's first one by the
+          // block kPyBlocks - 1 + n ahead of it, made from its predecessor
+          const int dst = (py_cur + done) & (kPyBlocks - 1);
+          const int src = (dst + kPyBlocks - 1) & (kPyBlocks - 1);
+          warp_twist<true>(sm.mt_py[src], sm.mt_py[dst], lane, dst, sm.py_nonce);
+          ++done;
+          __syncwarp();     // every lane's words and nonce bytes, then lane 0's release
+          if (lane == 0) st_rel_u32(&sm.mt_done, (uint32_t)done);
+          continue;
+        }
         const int idx = applied + lane;
         const unsigned long long raw = ld_rlx_u64(&sm.opq[idx % kOpQueue]);
         const bool ready = (uint32_t)(raw >> 56) == (uint32_t)((idx + 1) & 255) && raw != 0ull;
@@ -1484,78 +1512,16 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           // release: the queue slots just read may be rewritten by whoever sees this
           __syncwarp();
           if (lane == 0) st_rel_u32(&sm.applied_pub, (uint32_t)applied);
-        } else {
-          int st = 0, fin = 0;
-          if (lane == 0) {
-            st = (int)ld_acq_u32(&sm.stop);        // stop is set last, with a release
-            fin = (int)ld_rlx_u32(&sm.final_emitted);
-          }
-          st = __shfl_sync(kFull, st, 0);
-          fin = __shfl_sync(kFull, fin, 0);
-          if (st && applied >= fin) break;
-          __nanosleep(100);
+          continue;
         }
-      }
-    } else if (warp == kTwistWarp) {
-      int done = 0;
-      // Idle time goes into warming L2 for the next segment's scoring pass: its 8192
-      // table gathers are addressed by (source window, target window), and all but the
-      // few hundred cells this segment still rewrites already hold their final source
-      // bytes.  Prefetches only -- nothing is read back, so a stale address costs a miss
-      // later and nothing else.
-      const uint64_t* pf_tp = nullptr;
-      int pf_aux = 0, pf_col = 0;
-      // ... and, before that, into the stream N blocks the next heapify will draw from
-      // (one nonce per nonzero priority, video.py:259-267: 13 blocks for a full screen).
-      const int np_goal = (seg + 1 < n_segments && P <= kCells / 2) ? kNpPreMax : 0;
-      int np_made = 0;
-      if (seg + 1 < n_segments && segments[3 * seg + 5] > 0) {
-        pf_aux = segments[3 * seg + 4];
-        pf_tp = target_packed + ((size_t)clip * n_frames + segments[3 * seg + 3]) * kCols;
-      }
-      while (true) {
-        int req = 0, st = 0;
-        if (lane == 0) {
-          req = (int)ld_acq_u32(&sm.mt_req);    // acquire: the slot to overwrite has been read
-          st = (int)ld_rlx_u32(&sm.stop);
-        }
-        req = __shfl_sync(kFull, req, 0);
-        st = __shfl_sync(kFull, st, 0);
-        if (req > done) {
-          // request n (from 1) replaces the block n behind the segment's first one by the
-          // block kPyBlocks - 1 + n ahead of it, made from its predecessor
-          const int dst = (py_cur + done) & (kPyBlocks - 1);
-          const int src = (dst + kPyBlocks - 1) & (kPyBlocks - 1);
-          warp_twist<true>(sm.mt_py[src], sm.mt_py[dst], lane, dst, sm.py_nonce);
-          ++done;
-          __syncwarp();     // every lane's words and nonce bytes, then lane 0's release
-          if (lane == 0) st_rel_u32(&sm.mt_done, (uint32_t)done);
-        } else if (st) {
-          break;
-        } else if (np_made < np_goal) {
+        if (st && applied >= fin) break;
+        if (np_made < np_goal) {
           warp_twist<false>(np_made == 0 ? sm.mt_np[np_cur] : np_pre_blocks + (np_made - 1) * 624,
                             np_pre_blocks + np_made * 624, lane, 0, sm.py_nonce);
           ++np_made;
           if (lane == 0) st_rlx_u32(&sm.np_pre, (uint32_t)np_made);
-        } else if (pf_tp != nullptr && pf_col < kCols) {
-          uint64_t g[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) g[q] = __ldg(pf_tp + pf_col + 32 * q + lane);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint64_t s = ld_rlx_u64(&sm.src[pf_col + 32 * q + lane]);   // racy by design
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int o = byte_offset<MODE>(half, pf_aux);
-              const uint32_t x = mask_shift<MODE>(s, o), y = mask_shift<MODE>(g[q], o);
-              const uint16_t* addr =
-                  table + (((uint32_t)o << (2 * M::kBits)) + (x << M::kBits) + y);
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
-            }
-          }
-          pf_col += 128;
         } else {
-          __nanosleep(200);
+          __nanosleep(100);
         }
       }
     }
