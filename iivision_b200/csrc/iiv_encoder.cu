@@ -836,21 +836,23 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     //       (only stores to that page change what was read); then the warp re-digests
     //       the entry itself.  It draws the nonces, picks the two best offsets, updates
     //       priorities, re-queues, publishes the opcode: shared memory + shuffles only.
-    //   helper (warp 3)  two background jobs: it commits the stores of every published
+    //   helper (warp 4)  two background jobs: it commits the stores of every published
     //       opcode to the source bitmap and memory map (Bitmap.apply), in order -- nothing
     //       in phase B reads the source, so this is off the chain -- and it prepares the
-    //       next MT19937 block of stream P when asked and, when idle, the next segment's
-    //       stream N blocks.  (One warp instead of two: a polling warp costs its
-    //       scheduler's other warps issue slots -- 148 clips +9 %, a single clip +2 %.)
+    //       next MT19937 block of stream P when asked.  (One warp instead of two: a polling
+    //       warp costs its scheduler's other warps issue slots -- 148 clips +9 %, a single
+    //       clip +2 %.)
+    //   np (warp 3)  makes the stream N blocks the next segment's heapify will draw from,
+    //       then goes quiet.
     // A cell whose priority is already 0 is skipped by everyone alike: priorities only
     // ever fall to 0 inside a segment (video.py:140, :159-170).
     // The issue arbiter favours the highest warp id of a scheduler and a spinning warp
     // is nearly always eligible, hence the decision warp is 7 and shares its scheduler
-    // (warp id % 4) with the helper, which is idle or streaming through a block most of
-    // the time (swapping it with a producer measured the same); helper loops back off
-    // with nanosleep.  Warp 4 has no role in phase B.
+    // (warp id % 4) only with the np warp, which works for a tenth of a segment and never
+    // polls (with the helper on that scheduler instead a clip is 2.4 % slower); helper loops
+    // back off with nanosleep.
     constexpr uint32_t kFull = 0xffffffffu;
-    constexpr int kDecideWarp = 7, kHelpWarp = 3;
+        constexpr int kDecideWarp = 7, kHelpWarp = 4, kNpWarp = 3;
     constexpr uint32_t kKindLive = 0u, kKindDead = 1u, kKindEndOfHeap = 2u;
     if (t < kRing) {
       sm.ring_tag[t] = 0xffffffffu;
@@ -1449,8 +1451,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     } else if (warp == kHelpWarp) {
       // helper: two background jobs in one warp.
       //  * twister: prepares the next MT19937 block of stream P when the decision warp asks
-      //    for it and, in idle time, the stream N blocks the next heapify will draw from
-      //    (one nonce per nonzero priority, video.py:259-267: 13 blocks for a full screen);
+      //    for it;
       //  * applier: Bitmap.apply for (off, o1, o2) of each published record.  Stores only
       //    interact inside a page (a packed word and its two neighbours), so lane i takes
       //    the i-th pending record and records of different pages are applied at once;
@@ -1458,8 +1459,6 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
       //    offset that repeats offsets[0] is idempotent.  Nothing in phase B reads the
       //    source, and the queue is 64 records deep: a block twist in between is no matter.
       int done = 0, applied = 0;
-      const int np_goal = (seg + 1 < n_segments && P <= kCells / 2) ? kNpPreMax : 0;
-      int np_made = 0;
       while (true) {
         int req = 0, st = 0, fin = 0;
         if (lane == 0) {
@@ -1515,14 +1514,20 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
           continue;
         }
         if (st && applied >= fin) break;
-        if (np_made < np_goal) {
-          warp_twist<false>(np_made == 0 ? sm.mt_np[np_cur] : np_pre_blocks + (np_made - 1) * 624,
-                            np_pre_blocks + np_made * 624, lane, 0, sm.py_nonce);
-          ++np_made;
-          if (lane == 0) st_rlx_u32(&sm.np_pre, (uint32_t)np_made);
-        } else {
-          __nanosleep(100);
-        }
+        __nanosleep(100);
+      }
+    } else if (warp == kNpWarp) {
+      // the stream N blocks the next heapify will draw from (one nonce per nonzero priority,
+      // video.py:259-267: 13 blocks for a full screen), one after the other, then nothing:
+      // this warp shares the decision warp's scheduler and must not poll
+      const int np_goal = (seg + 1 < n_segments && P <= kCells / 2) ? kNpPreMax : 0;
+      for (int np_made = 0; np_made < np_goal; ++np_made) {
+        int st = 0;
+        if (lane == 0) st = (int)ld_rlx_u32(&sm.stop);
+        if (__shfl_sync(kFull, st, 0)) break;
+        warp_twist<false>(np_made == 0 ? sm.mt_np[np_cur] : np_pre_blocks + (np_made - 1) * 624,
+                          np_pre_blocks + np_made * 624, lane, 0, sm.py_nonce);
+        if (lane == 0) st_rlx_u32(&sm.np_pre, (uint32_t)(np_made + 1));
       }
     }
     __syncthreads();
