@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("IIV_LIB_PATH") or os.path.join(_HERE, "libiivision_b2
 
 MODE_HGR, MODE_DHGR = 0, 1
 LAYOUT_TRIANGULAR, LAYOUT_SYMMETRIC = 0, 1
-ALGO_AUTO, ALGO_CHAIN, ALGO_TREE = 0, 1, 2
+ALGO_AUTO, ALGO_CHAIN, ALGO_TREE, ALGO_SPLIT = 0, 1, 2, 3
 CLIP_STATE_FIELDS = 8
 
 c_int, c_size_t, c_void_p = ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p
@@ -34,6 +34,7 @@ PROTOTYPES = {
     "iiv_all_pixel_strings": (c_int, [c_int, c_void_p, c_void_p]),
     "iiv_table_generate": (c_int, [c_int, c_void_p, c_void_p, c_u32, c_u32,
                                    c_int, c_int, c_void_p]),
+    "iiv_table_split_windows": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "iiv_table_generate_scatter": (c_int, [c_int, c_void_p, c_void_p, c_int,
                                            c_int, c_void_p, c_u32, c_u32, c_int,
                                            c_void_p]),

@@ -8,8 +8,9 @@
 // clips.  Inside a block the segment runs in two phases: phase A (all 256 threads)
 // scores the bank, draws the heap nonces, radix-selects the reachable prefix of the
 // heap and sorts it; phase B cuts the loop into stages run by specialised warps --
-// row producers, speculative front ends, one decision warp, an applier and an MT19937
-// twister -- that talk through flag-guarded rings in shared memory (see phase B below).
+// row producers, speculative front ends, one decision warp, a helper (applier + MT19937
+// twister) and a preparer of the next segment -- that talk through released / acquired
+// words and rings in shared memory (see phase B below).
 //
 // Exactness notes:
 //  * heapq pops the smallest (-priority, nonce, page, offset) tuple; with unique
@@ -372,8 +373,8 @@ __device__ __forceinline__ void apply_store(uint64_t* src, uint8_t* mem, int pag
                                             int offset, int is_aux, uint32_t value) {
   const int o = byte_offset<MODE>(offset, is_aux);
   const int c = offset >> 1;
-  // relaxed stores: the applier is the only writer in phase B, but the twister reads these
-  // words (for prefetch addresses only) while they change
+  // relaxed stores: the helper warp is the only writer in phase B, but the stream-N warp
+  // reads these words (for prefetch addresses only) while they change
   uint64_t* row = src + page * 128;
   const uint64_t w = masked_update<MODE>(o, row[c], value);
   st_rlx_u64(&row[c], w);
@@ -431,7 +432,7 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
     sm.mt_py[0][k] = g_mt_py[k];
   }
   int np_cur = 0;                 // which ping-pong buffer holds stream N
-  // Successor blocks of stream N that the twister warp generated during the previous
+  // Successor blocks of stream N that the stream-N warp generated during the previous
   // segment's opcode loop; they live in the upper half of the heap array, which phase B
   // does not use when the sorted prefix is at most 4096 keys.
   constexpr int kNpPreMax = 13;   // (623 + 7680 - 1) / 624 blocks at most per segment
@@ -962,8 +963,8 @@ encode_kernel(uint8_t* __restrict__ states, size_t state_stride,
         if (pos_py > 624) {
           if (mt_seen < mt_issued - 1) {
             const long long c0 = clock64();
-            // the twister shares this warp's scheduler: sleep rather than spin, or the
-            // poll starves the very warp it is waiting for
+            // back off rather than spin (the helper that makes the block is on another
+            // scheduler, but a spin costs power and the wake-up is not on a tight path)
             // acquire: the block's nonce bytes are read after the flag
             while ((mt_seen = (int)ld_acq_u32(&sm.mt_done)) < mt_issued - 1) __nanosleep(40);
             wait_mt += clock64() - c0;

@@ -11,6 +11,8 @@
 //     D_t = min(D_{t-1} + S[a_t][b_t],  D_{t-2} + 1 if a_{t-1}==b_t && a_t==b_{t-1})
 // (tests/test_oracle_tables.py checks the collapse against the
 // restated full DP).  All arithmetic is exact small-integer work.
+#include <mutex>
+
 #include "iiv_common.cuh"
 
 namespace iiv {
@@ -471,6 +473,277 @@ tree_kernel(const __grid_constant__ Lut lut, const __grid_constant__ Dests dests
   }
 }
 
+// ---- ALGO_SPLIT: the chain cut in two, each half tabulated -------------------------
+// The recurrence is a product of 2x2 (min,+) matrices, one per pixel, so it can be cut
+// at pixel c:
+//     entry = min(D_c + F_c,  D_{c-1} + 1 + F_{c+1} if pixels (c-1, c) are a swapped pair)
+// with D the forward form over pixels 0..c-1 (chain_kernel) and F the backward form over
+// pixels c..n-1 (tree_kernel).  Pixel t is a rotation of dots t..t+3 (colours.py:100-134),
+// and a dot is fed by few bits of the masked value (screen.py:741-789), so each half
+// depends on a WINDOW of the value's bits only:
+//     HGR  (c = 8): pixels 0..8 <- 9 bits (header, palette bit, low body), pixels 8..17 <- 9
+//     DHGR (c = 4): pixels 0..4 <- bits 0..7,                       pixels 4..9  <- bits 4..12
+// (tests/test_oracle_tables.py::test_split_windows checks the windows against the oracle's
+// pixel strings).  split_prologue tabulates A = (D_c, D_{c-1}+1 | INF) over pairs of A
+// windows and B = (F_c, F_{c+1}) over pairs of B windows -- 2^16..2^18 pairs per offset
+// instead of 2^26 / 2^28 -- and an entry of the big table is then one packed add and one
+// VIADDMNMX.U16x2 for two entries: the generator is a write stream.
+//
+// A thread owns 8 consecutive j inside the A window (their 8 A pairs stay in registers)
+// and walks the 32 values of the 5 bits of j outside that window; every step is one
+// 4-byte load of B (L1), two byte permutes, 8 packed ALU ops and one 16-byte store; a
+// warp's 32 threads cover 256 consecutive j, so every store instruction writes 512
+// contiguous bytes.
+constexpr int kSplitThreads = 256;
+constexpr uint32_t kSplitInf = 0x4000;   // + any F stays below 0x8000 (n * 255 <= 4590)
+
+__host__ __device__ constexpr int ctz_c(uint32_t x) {
+  int n = 0;
+  while (n < 32 && !((x >> n) & 1u)) ++n;
+  return n;
+}
+
+// Compile-time bit window of at most two runs: ext gathers the window's bits of v into a
+// dense index (lowest bit first), dep scatters an index back.
+template <uint32_t MASK>
+struct Bits {
+  static constexpr int lo1 = ctz_c(MASK);
+  static constexpr int len1 = ctz_c(~(MASK >> lo1));
+  static constexpr uint32_t rest = MASK & ~(((1u << len1) - 1u) << lo1);
+  static constexpr int lo2 = rest ? ctz_c(rest) : 0;
+  static constexpr int len2 = rest ? ctz_c(~(rest >> lo2)) : 0;
+  static_assert(rest == (((1u << len2) - 1u) << lo2), "window of at most two runs");
+  static constexpr int count = len1 + len2;
+  __host__ __device__ static __forceinline__ constexpr uint32_t ext(uint32_t v) {
+    return ((v >> lo1) & ((1u << len1) - 1u)) |
+           (len2 ? ((v >> lo2) & ((1u << len2) - 1u)) << len1 : 0u);
+  }
+  __host__ __device__ static __forceinline__ constexpr uint32_t dep(uint32_t x) {
+    return ((x & ((1u << len1) - 1u)) << lo1) |
+           (len2 ? ((x >> len1) & ((1u << len2) - 1u)) << lo2 : 0u);
+  }
+};
+
+// Windows per (mode, window set).  HGR has one set per offset (the palette bit that shifts
+// the body's dots is bit 10 at offset 0 and bit 3 at offset 1); DHGR's dots are the value.
+template <int MODE, int WIN>
+struct SplitWin;
+template <>
+struct SplitWin<IIV_MODE_HGR, 0> {
+  static constexpr int kCut = 8;
+  static constexpr uint32_t kMaskA = 0x04ff, kMaskB = 0x3fe0;
+};
+template <>
+struct SplitWin<IIV_MODE_HGR, 1> {
+  static constexpr int kCut = 8;
+  static constexpr uint32_t kMaskA = 0x01ff, kMaskB = 0x3fc8;
+};
+template <>
+struct SplitWin<IIV_MODE_DHGR, 0> {
+  static constexpr int kCut = 4;
+  static constexpr uint32_t kMaskA = 0x00ff, kMaskB = 0x1ff0;
+};
+template <int MODE>
+struct SplitDims {
+  static constexpr int kWins = MODE == IIV_MODE_HGR ? 2 : 1;   // window sets
+  static constexpr int kA = Bits<SplitWin<MODE, 0>::kMaskA>::count;
+  static constexpr int kB = Bits<SplitWin<MODE, 0>::kMaskB>::count;
+  static constexpr size_t kWordsA = (size_t)Mode<MODE>::kOffsets << (2 * kA);   // uint16 pairs
+  static constexpr size_t kWordsB = (size_t)Mode<MODE>::kOffsets << (2 * kB);   // uint32
+};
+
+// A[o][xi][0][xj] = D_c, A[o][xi][1][xj] = D_{c-1} + 1 or INF (uint16);
+// B[o][yi][yj] = F_c | F_{c+1} << 16.
+template <int MODE, int WIN>
+__device__ __forceinline__ void split_tabulate(const uint8_t* S, int o, int which, uint32_t idx,
+                                               uint16_t* ta, uint32_t* tb) {
+  using M = Mode<MODE>;
+  using W = SplitWin<MODE, WIN>;
+  using BA = Bits<W::kMaskA>;
+  using BB = Bits<W::kMaskB>;
+  constexpr int n = M::kDots, c = W::kCut;
+  uint64_t alo, blo;
+  uint32_t ahi, bhi;
+  if (which == 0) {
+    constexpr uint32_t NA = 1u << BA::count;
+    if (idx >= NA * NA) return;
+    const uint32_t xi = idx >> BA::count, xj = idx & (NA - 1u);
+    load_pixels<MODE>(o, BA::dep(xi), alo, ahi);
+    load_pixels<MODE>(o, BA::dep(xj), blo, bhi);
+    uint32_t d2 = 0, d1 = 0, pa = 0, pb = 0;
+#pragma unroll
+    for (int t = 0; t < c; ++t) {
+      const uint32_t a = pixel_at(alo, ahi, t), b = pixel_at(blo, bhi, t);
+      uint32_t cur = d1 + S[a * 16 + b];
+      if (t >= 1 && pa == b && a == pb) cur = min(cur, d2 + 1u);
+      d2 = d1; d1 = cur; pa = a; pb = b;
+    }
+    const uint32_t a = pixel_at(alo, ahi, c), b = pixel_at(blo, bhi, c);
+    uint16_t* row = ta + (((size_t)o * NA + xi) * 2) * NA + xj;
+    row[0] = (uint16_t)d1;
+    row[NA] = (uint16_t)((pa == b && a == pb) ? d2 + 1u : kSplitInf);
+  } else {
+    constexpr uint32_t NB = 1u << BB::count;
+    if (idx >= NB * NB) return;
+    const uint32_t yi = idx >> BB::count, yj = idx & (NB - 1u);
+    load_pixels<MODE>(o, BB::dep(yi), alo, ahi);
+    load_pixels<MODE>(o, BB::dep(yj), blo, bhi);
+    uint32_t f1 = 0, f2 = 0, na = 0, nb = 0;   // F_{t+1}, F_{t+2}, pixels t+1
+#pragma unroll
+    for (int t = n - 1; t >= c; --t) {
+      const uint32_t a = pixel_at(alo, ahi, t), b = pixel_at(blo, bhi, t);
+      uint32_t cur = f1 + S[a * 16 + b];
+      if (t + 1 < n && a == nb && na == b) cur = min(cur, f2 + 1u);
+      f2 = f1; f1 = cur; na = a; nb = b;
+    }
+    tb[((size_t)o * NB + yi) * NB + yj] = f1 | (f2 << 16);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+split_prologue(const __grid_constant__ Lut lut, uint16_t* __restrict__ ta,
+               uint32_t* __restrict__ tb) {
+  __shared__ uint8_t S[256];
+  S[threadIdx.x] = lut.s[threadIdx.x];
+  __syncthreads();
+  const int o = blockIdx.z, which = blockIdx.y;
+  const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
+  if (MODE == IIV_MODE_HGR && o == 1)
+    split_tabulate<MODE, SplitDims<MODE>::kWins - 1>(S, o, which, idx, ta, tb);
+  else
+    split_tabulate<MODE, 0>(S, o, which, idx, ta, tb);
+}
+
+template <int MODE, int WIN, bool TRI, bool MULTI>
+__device__ __forceinline__ void split_rows(int o, const uint16_t* __restrict__ ta,
+                                           const uint32_t* __restrict__ tb, const Dests& dests,
+                                           uint32_t row_begin, uint32_t row_end) {
+  using M = Mode<MODE>;
+  using W = SplitWin<MODE, WIN>;
+  using BA = Bits<W::kMaskA>;
+  using BB = Bits<W::kMaskB>;
+  using BO = Bits<~W::kMaskA & ((1u << M::kBits) - 1u)>;   // the bits of j outside A's window
+  static_assert((W::kMaskA & 0xffu) == 0xffu, "a warp's 32 octets are 256 consecutive j");
+  static_assert((W::kMaskB & 7u) == 0u, "B is constant over an octet of j");
+  constexpr uint32_t NA = 1u << BA::count, NB = 1u << BB::count;
+  constexpr int kThreadsPerRow = NA / 8, kRows = kSplitThreads / kThreadsPerRow;
+
+  const uint32_t i = row_begin + blockIdx.x * kRows + threadIdx.x / kThreadsPerRow;
+  if (i >= row_end) return;
+  const uint32_t xj = (threadIdx.x % kThreadsPerRow) * 8;   // A index of the octet's first j
+  const uint32_t jb = BA::dep(xj);                          // that j, outside bits zero
+  const uint16_t* arow = ta + (((size_t)o * NA + BA::ext(i)) * 2) * NA + xj;
+  const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(arow));
+  const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(arow + NA));
+  const uint32_t* brow = tb + ((size_t)o * NB + BB::ext(i)) * NB + BB::ext(jb);
+  const size_t at = ((size_t)o << (2 * M::kBits)) + ((size_t)i << M::kBits) + jb;
+  const int below = (int)i - (int)jb;   // entries j < i of the octet at jb + J: below - J
+
+#pragma unroll
+  for (uint32_t e = 0; e < (1u << BO::count); ++e) {
+    const uint32_t J = BO::dep(e);   // compile-time after unrolling
+    uint4 v;
+    if (TRI && below - (int)J <= 0) {
+      v = make_uint4(0, 0, 0, 0);
+    } else {
+      const uint32_t b = __ldg(brow + BB::ext(J));
+      const uint32_t b0 = __byte_perm(b, 0, 0x1010), b1 = __byte_perm(b, 0, 0x3232);
+      v.x = __viaddmin_u16x2(a1.x, b1, a0.x + b0);
+      v.y = __viaddmin_u16x2(a1.y, b1, a0.y + b0);
+      v.z = __viaddmin_u16x2(a1.z, b1, a0.z + b0);
+      v.w = __viaddmin_u16x2(a1.w, b1, a0.w + b0);
+      if (TRI && below - (int)J < 8) {
+        const int d = below - (int)J;
+        v.x &= (0 < d ? 0xffffu : 0u) | (1 < d ? 0xffff0000u : 0u);
+        v.y &= (2 < d ? 0xffffu : 0u) | (3 < d ? 0xffff0000u : 0u);
+        v.z &= (4 < d ? 0xffffu : 0u) | (5 < d ? 0xffff0000u : 0u);
+        v.w &= (6 < d ? 0xffffu : 0u) | (7 < d ? 0xffff0000u : 0u);
+      }
+    }
+    if (MULTI) {
+      if (dests.multicast) {
+        multimem_st_v4(dests.p[0] + at + J, v);
+      } else {
+        for (int dd = 0; dd < dests.n; ++dd)
+          *reinterpret_cast<uint4*>(dests.p[dd] + at + J) = v;
+      }
+    } else {
+      *reinterpret_cast<uint4*>(dests.p[0] + at + J) = v;
+    }
+  }
+}
+
+template <int MODE, bool TRI, bool MULTI>
+__global__ void __launch_bounds__(kSplitThreads)
+split_kernel(const uint16_t* __restrict__ ta, const uint32_t* __restrict__ tb,
+             const __grid_constant__ Dests dests, uint32_t row_begin, uint32_t row_end) {
+  const int o = blockIdx.y;
+  if (MODE == IIV_MODE_HGR && o == 1)
+    split_rows<MODE, SplitDims<MODE>::kWins - 1, TRI, MULTI>(o, ta, tb, dests, row_begin, row_end);
+  else
+    split_rows<MODE, 0, TRI, MULTI>(o, ta, tb, dests, row_begin, row_end);
+}
+
+// Scratch for the A / B tables of one generate call: stream-ordered allocations from a pool
+// the library keeps per device (release threshold unlimited, so a steady stream of calls
+// allocates nothing).  The tables depend on the LUT, so they cannot live in __device__
+// globals shared by concurrent calls.
+int split_scratch(void** p, size_t bytes, cudaStream_t st) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  IIV_CUDA(cudaGetDevice(&dev));
+  IIV_REQUIRE(dev >= 0 && dev < 64, "device %d out of range", dev);
+  cudaMemPool_t pool;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      IIV_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+      uint64_t keep = ~(uint64_t)0;
+      IIV_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    pool = pools[dev];
+  }
+  IIV_CUDA(cudaMallocFromPoolAsync(p, bytes, pool, st));
+  return 0;
+}
+
+template <int MODE>
+int generate_split(const Lut& lut, const Dests& dests, uint32_t row_begin, uint32_t row_end,
+                   bool tri, bool multi, cudaStream_t st) {
+  using M = Mode<MODE>;
+  using D = SplitDims<MODE>;
+  constexpr size_t bytes_a = D::kWordsA * 2 * sizeof(uint16_t), bytes_b = D::kWordsB * 4;
+  void* scratch = nullptr;
+  const int rc = split_scratch(&scratch, bytes_a + bytes_b, st);
+  if (rc) return rc;
+  uint16_t* ta = reinterpret_cast<uint16_t*>(scratch);
+  uint32_t* tb = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + bytes_a);
+  constexpr uint32_t pairs = 1u << (2 * (D::kA > D::kB ? D::kA : D::kB));
+  split_prologue<MODE><<<dim3(pairs / 256, 2, M::kOffsets), 256, 0, st>>>(lut, ta, tb);
+  constexpr int rows_per_block = kSplitThreads / ((1 << D::kA) / 8);
+  dim3 grid((row_end - row_begin + rows_per_block - 1) / rows_per_block, M::kOffsets);
+  if (tri && multi)
+    split_kernel<MODE, true, true><<<grid, kSplitThreads, 0, st>>>(ta, tb, dests, row_begin, row_end);
+  else if (tri)
+    split_kernel<MODE, true, false><<<grid, kSplitThreads, 0, st>>>(ta, tb, dests, row_begin, row_end);
+  else if (multi)
+    split_kernel<MODE, false, true><<<grid, kSplitThreads, 0, st>>>(ta, tb, dests, row_begin, row_end);
+  else
+    split_kernel<MODE, false, false><<<grid, kSplitThreads, 0, st>>>(ta, tb, dests, row_begin, row_end);
+  const cudaError_t launched = cudaGetLastError();
+  const cudaError_t freed = cudaFreeAsync(scratch, st);
+  if (launched != cudaSuccess) return cuda_fail(launched, "split_kernel");
+  if (freed != cudaSuccess) return cuda_fail(freed, "cudaFreeAsync");
+  return 0;
+}
+
 // edit_distance (make_data_tables.py:92-108) for explicit pixel strings: pairs of
 // `len` nibble-valued pixels, one thread per pair.
 __global__ void string_distance_kernel(Lut32 lut, const uint8_t* __restrict__ a,
@@ -543,10 +816,11 @@ int generate(const Lut& lut, const Dests& dests, uint32_t row_begin,
     IIV_LAUNCH_CHECK("chain_kernel");
     return 0;
   }
+  const bool tri = layout == IIV_LAYOUT_TRIANGULAR, multi = dests.n > 1 || dests.multicast;
+  if (algo != IIV_ALGO_TREE) return generate_split<MODE>(lut, dests, row_begin, row_end, tri, multi, st);
   const uint32_t tiles = ((row_end + 7) >> 3) - (row_begin >> 3);
   dim3 grid(N / (kTreeThreads * 8), (tiles + kTilesPerChunk - 1) / kTilesPerChunk,
             M::kOffsets);
-  const bool tri = layout == IIV_LAYOUT_TRIANGULAR, multi = dests.n > 1 || dests.multicast;
   if (tri && multi)
     tree_kernel<MODE, true, true><<<grid, kTreeThreads, 0, st>>>(lut, dests, row_begin, row_end);
   else if (tri)
@@ -616,6 +890,26 @@ static int generate_any(int mode, const int32_t* h_lut, const Dests& dests,
   if (mode == IIV_MODE_DHGR)
     return generate<IIV_MODE_DHGR>(lut, dests, row_begin, row_end, layout, algo, st);
   IIV_REQUIRE(false, "bad mode %d", mode);
+}
+
+// The bit windows ALGO_SPLIT cuts the masked value into (host-only query: the CPU tests
+// check them against the oracle's pixel strings).
+extern "C" int iiv_table_split_windows(int mode, int offset, int* cut, uint32_t* mask_a,
+                                       uint32_t* mask_b) {
+  IIV_REQUIRE(cut && mask_a && mask_b, "null pointer");
+  if (mode == IIV_MODE_HGR && offset == 0) {
+    using W = SplitWin<IIV_MODE_HGR, 0>;
+    *cut = W::kCut; *mask_a = W::kMaskA; *mask_b = W::kMaskB;
+  } else if (mode == IIV_MODE_HGR && offset == 1) {
+    using W = SplitWin<IIV_MODE_HGR, 1>;
+    *cut = W::kCut; *mask_a = W::kMaskA; *mask_b = W::kMaskB;
+  } else if (mode == IIV_MODE_DHGR && offset >= 0 && offset < 4) {
+    using W = SplitWin<IIV_MODE_DHGR, 0>;
+    *cut = W::kCut; *mask_a = W::kMaskA; *mask_b = W::kMaskB;
+  } else {
+    IIV_REQUIRE(false, "bad mode %d / offset %d", mode, offset);
+  }
+  return 0;
 }
 
 extern "C" int iiv_table_generate(int mode, const int32_t* h_lut,

@@ -129,12 +129,13 @@ def fill_probe(buf: torch.Tensor, variant: int = 0) -> None:
 
 
 def launches_per_table_generate() -> int:
-    """Kernels one iiv_table_generate call launches (pixel prologue + generator)."""
-    return 2
+    """Kernels one iiv_table_generate call launches (pixel strings, the split generator's
+    A / B tables, the generator)."""
+    return 3
 
 
 def generator_kernel_name() -> str:
-    return "tree_kernel"
+    return "split_kernel"
 
 
 def table_generate_into(mode, lut, layout, row_begin, row_end,

@@ -48,6 +48,7 @@ extern "C" {
 #define IIV_ALGO_AUTO 0
 #define IIV_ALGO_CHAIN 1 /* one independent 1-D recurrence per entry */
 #define IIV_ALGO_TREE 2  /* shared-suffix tree over a block of j per thread */
+#define IIV_ALGO_SPLIT 3 /* chain cut in two tabulated halves (what AUTO runs) */
 
 const char* iiv_last_error(void);
 int iiv_version(void);
@@ -93,6 +94,13 @@ int iiv_all_pixel_strings(int mode, uint8_t* d_pix, void* stream);
 int iiv_table_generate(int mode, const int32_t* h_lut, uint16_t* d_table,
                        uint32_t row_begin, uint32_t row_end, int layout,
                        int algo, void* stream);
+
+/* No reference counterpart (host-only, no device needed): the bit windows of the masked
+ * value that IIV_ALGO_SPLIT's two halves of edit_distance (make_data_tables.py:92-108)
+ * depend on at `offset` -- pixels 0..cut of colours.py:137-148's string are functions of
+ * the bits in mask_a only, pixels cut..n-1 of the bits in mask_b only. */
+int iiv_table_split_windows(int mode, int offset, int* cut, uint32_t* mask_a,
+                            uint32_t* mask_b);
 
 /* edit_distance (make_data_tables.py:92-108) for n_pairs explicit pixel strings
  * of `len` nibble-valued pixels each (d_a, d_b: uint8[n_pairs][len]); d_out

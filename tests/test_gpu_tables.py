@@ -55,7 +55,7 @@ def test_tree_kernel_equals_chain_kernel(ops, oracle_luts, mode, layout):
     """The shared-suffix tree generator against the one-chain-per-entry kernel,
     with an adversarial LUT (zeros off the diagonal, values up to 255)."""
     import torch
-    from iivision_b200._lib import ALGO_CHAIN, ALGO_TREE
+    from iivision_b200._lib import ALGO_CHAIN, ALGO_SPLIT, ALGO_TREE
     rng = np.random.default_rng(11)
     lut = rng.integers(0, 256, size=(16, 16)).astype(np.int32)
     lut = np.minimum(lut, lut.T)
@@ -66,6 +66,43 @@ def test_tree_kernel_equals_chain_kernel(ops, oracle_luts, mode, layout):
         a = ops.table_generate(mode, table_lut, layout=layout, algo=ALGO_CHAIN)
         b = ops.table_generate(mode, table_lut, layout=layout, algo=ALGO_TREE)
         assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+        del b
+        c = ops.table_generate(mode, table_lut, layout=layout, algo=ALGO_SPLIT)
+        assert torch.equal(a.view(torch.int16), c.view(torch.int16))
+
+
+def test_split_kernel_extreme_luts(ops):
+    """The split generator's packed 16-bit arithmetic at its limits: every substitution
+    costs 255 (entries up to n * 255, the INF marker of an absent swap must never win),
+    and a LUT of zeros (every entry 0 or a swap's 1)."""
+    import torch
+    from iivision_b200._lib import ALGO_CHAIN, ALGO_SPLIT
+    hi = np.full((16, 16), 255, dtype=np.int32)
+    np.fill_diagonal(hi, 0)
+    for lut in (hi, np.full((16, 16), 255, dtype=np.int32), np.zeros((16, 16), dtype=np.int32)):
+        for mode in ("HGR", "DHGR"):
+            a = ops.table_generate(mode, lut, layout=1, algo=ALGO_CHAIN)
+            c = ops.table_generate(mode, lut, layout=1, algo=ALGO_SPLIT)
+            assert torch.equal(a.view(torch.int16), c.view(torch.int16))
+            del a, c
+
+
+def test_concurrent_generates_on_two_streams(ops, oracle_luts):
+    """Two generate calls with different LUTs in flight at once (the split generator's
+    scratch tables are per call, not globals)."""
+    import torch
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    want = {pid: ops.table_generate("DHGR", oracle_luts[pid]) for pid in (5, 0)}
+    outs = {pid: torch.empty_like(want[pid]) for pid in (5, 0)}
+    torch.cuda.synchronize()
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            ops.table_generate("DHGR", oracle_luts[5], out=outs[5])
+        with torch.cuda.stream(s2):
+            ops.table_generate("DHGR", oracle_luts[0], out=outs[0])
+    torch.cuda.synchronize()
+    for pid in (5, 0):
+        assert torch.equal(outs[pid].view(torch.int16), want[pid].view(torch.int16))
 
 
 def test_row_ranges_unaligned(ops, oracle_luts):

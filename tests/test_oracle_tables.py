@@ -173,3 +173,32 @@ def test_low_bits_reach_leaf_pixels_only(mode, leaf):
         for bit in range(3):
             dep = {t for t in range(n) if (pix[o][v, t] != pix[o][v ^ (1 << bit), t]).any()}
             assert dep <= want[bit] and max(dep) < leaf, (mode, o, bit, dep)
+
+
+@pytest.mark.parametrize("mode", ["HGR", "DHGR"])
+def test_split_windows(mode):
+    """The structural fact the split generator (csrc/iiv_tables.cu, ALGO_SPLIT) relies on:
+    pixels 0..cut of a value's string are functions of the bits in mask_a only, pixels
+    cut..n-1 of the bits in mask_b only -- the windows the library reports (host-only
+    call) against the oracle's pixel strings."""
+    import ctypes
+    from iivision_b200 import _lib
+    pix = tables.all_pixel_strings(mode)
+    bits, n = tables.MASKED_BITS[mode], tables.MASKED_DOTS[mode]
+    v = np.arange(1 << bits)
+    for o in range(pix.shape[0]):
+        cut, ma, mb = ctypes.c_int(), ctypes.c_uint32(), ctypes.c_uint32()
+        _lib.check(_lib.lib.iiv_table_split_windows(
+            tables.MODES[mode], o,
+            ctypes.byref(cut), ctypes.byref(ma), ctypes.byref(mb)))
+        cut, ma, mb = cut.value, ma.value, mb.value
+        assert 0 < cut < n - 1 and ma < (1 << bits) and mb < (1 << bits)
+        assert np.array_equal(pix[o][v, :cut + 1], pix[o][v & ma, :cut + 1]), (mode, o)
+        assert np.array_equal(pix[o][v, cut:], pix[o][v & mb, cut:]), (mode, o)
+        # what the kernel's thread mapping assumes about the windows
+        assert ma & 0xff == 0xff and mb & 7 == 0
+        assert bin(ma).count("1") + 5 == bits
+    with pytest.raises(_lib.IIVError):
+        _lib.check(_lib.lib.iiv_table_split_windows(0, 2, ctypes.byref(ctypes.c_int()),
+                                                    ctypes.byref(ctypes.c_uint32()),
+                                                    ctypes.byref(ctypes.c_uint32())))
