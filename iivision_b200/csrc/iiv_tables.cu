@@ -51,9 +51,38 @@ __device__ __forceinline__ void multimem_st_v4(uint16_t* addr, uint4 v) {
                : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with pdl_launch may start while
+// its predecessor in the stream still runs -- it waits in grid_dependency_wait() before it
+// touches anything the predecessor writes, and a predecessor calls launch_dependents() as
+// soon as letting the successor's blocks queue up cannot hurt it.  Launched the ordinary
+// way both calls are no-ops.
+__device__ __forceinline__ void grid_dependency_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st,
+                       Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <int MODE>
 __global__ void pixel_prologue() {
   using M = Mode<MODE>;
+  launch_dependents();
   const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
   const int o = blockIdx.y;
   if (v >= (1u << M::kBits)) return;
@@ -494,7 +523,17 @@ tree_kernel(const __grid_constant__ Lut lut, const __grid_constant__ Dests dests
 // 4-byte load of B (L1), two byte permutes, 8 packed ALU ops and one 16-byte store; a
 // warp's 32 threads cover 256 consecutive j, so every store instruction writes 512
 // contiguous bytes.
-constexpr int kSplitThreads = 256;
+#ifndef IIV_SPLIT_THREADS
+#define IIV_SPLIT_THREADS 256
+#endif
+#ifndef IIV_SPLIT_EPT
+#define IIV_SPLIT_EPT 4
+#endif
+#ifndef IIV_SPLIT_MIN_BLOCKS
+#define IIV_SPLIT_MIN_BLOCKS 8
+#endif
+constexpr int kSplitThreads = IIV_SPLIT_THREADS;
+constexpr int kSplitEpt = IIV_SPLIT_EPT;   // values of the outside bits one thread walks
 constexpr uint32_t kSplitInf = 0x4000;   // + any F stays below 0x8000 (n * 255 <= 4590)
 
 __host__ __device__ constexpr int ctz_c(uint32_t x) {
@@ -526,22 +565,25 @@ struct Bits {
 
 // Windows per (mode, window set).  HGR has one set per offset (the palette bit that shifts
 // the body's dots is bit 10 at offset 0 and bit 3 at offset 1); DHGR's dots are the value.
+// kLateA: two bits of A's window that reach no pixel before kSharedA; kEarlyB: two bits of
+// B's window that reach no pixel from kSharedB on -- the prologue walks the part of a chain
+// those bits cannot change once for their four values.
 template <int MODE, int WIN>
 struct SplitWin;
 template <>
 struct SplitWin<IIV_MODE_HGR, 0> {
-  static constexpr int kCut = 8;
-  static constexpr uint32_t kMaskA = 0x04ff, kMaskB = 0x3fe0;
+  static constexpr int kCut = 8, kSharedA = 6, kSharedB = 12;
+  static constexpr uint32_t kMaskA = 0x04ff, kMaskB = 0x3fe0, kLateA = 0x00c0, kEarlyB = 0x0060;
 };
 template <>
 struct SplitWin<IIV_MODE_HGR, 1> {
-  static constexpr int kCut = 8;
-  static constexpr uint32_t kMaskA = 0x01ff, kMaskB = 0x3fc8;
+  static constexpr int kCut = 8, kSharedA = 6, kSharedB = 12;
+  static constexpr uint32_t kMaskA = 0x01ff, kMaskB = 0x3fc8, kLateA = 0x0180, kEarlyB = 0x00c0;
 };
 template <>
 struct SplitWin<IIV_MODE_DHGR, 0> {
-  static constexpr int kCut = 4;
-  static constexpr uint32_t kMaskA = 0x00ff, kMaskB = 0x1ff0;
+  static constexpr int kCut = 4, kSharedA = 3, kSharedB = 6;
+  static constexpr uint32_t kMaskA = 0x00ff, kMaskB = 0x1ff0, kLateA = 0x00c0, kEarlyB = 0x0030;
 };
 template <int MODE>
 struct SplitDims {
@@ -553,7 +595,8 @@ struct SplitDims {
 };
 
 // A[o][xi][0][xj] = D_c, A[o][xi][1][xj] = D_{c-1} + 1 or INF (uint16);
-// B[o][yi][yj] = F_c | F_{c+1} << 16.
+// B[o][yi][yj] = F_c | F_{c+1} << 16.  A thread takes one xi (yi) and the four xj (yj) that
+// differ in the late (early) bits.
 template <int MODE, int WIN>
 __device__ __forceinline__ void split_tabulate(const uint8_t* S, int o, int which, uint32_t idx,
                                                uint16_t* ta, uint32_t* tb) {
@@ -562,41 +605,72 @@ __device__ __forceinline__ void split_tabulate(const uint8_t* S, int o, int whic
   using BA = Bits<W::kMaskA>;
   using BB = Bits<W::kMaskB>;
   constexpr int n = M::kDots, c = W::kCut;
-  uint64_t alo, blo;
-  uint32_t ahi, bhi;
+  uint64_t alo, blo[4];
+  uint32_t ahi, bhi[4];
   if (which == 0) {
-    constexpr uint32_t NA = 1u << BA::count;
-    if (idx >= NA * NA) return;
-    const uint32_t xi = idx >> BA::count, xj = idx & (NA - 1u);
+    constexpr uint32_t NA = 1u << BA::count, late = BA::ext(W::kLateA);
+    using BL = Bits<late>;
+    using BR = Bits<~late & (NA - 1u)>;
+    static_assert(BL::count == 2, "two late bits");
+    if (idx >= NA * NA / 4) return;
+    const uint32_t xi = idx / (NA / 4), xj0 = BR::dep(idx % (NA / 4));
     load_pixels<MODE>(o, BA::dep(xi), alo, ahi);
-    load_pixels<MODE>(o, BA::dep(xj), blo, bhi);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) load_pixels<MODE>(o, BA::dep(xj0 | BL::dep(v)), blo[v], bhi[v]);
     uint32_t d2 = 0, d1 = 0, pa = 0, pb = 0;
 #pragma unroll
-    for (int t = 0; t < c; ++t) {
-      const uint32_t a = pixel_at(alo, ahi, t), b = pixel_at(blo, bhi, t);
+    for (int t = 0; t < W::kSharedA; ++t) {
+      const uint32_t a = pixel_at(alo, ahi, t), b = pixel_at(blo[0], bhi[0], t);
       uint32_t cur = d1 + S[a * 16 + b];
       if (t >= 1 && pa == b && a == pb) cur = min(cur, d2 + 1u);
       d2 = d1; d1 = cur; pa = a; pb = b;
     }
-    const uint32_t a = pixel_at(alo, ahi, c), b = pixel_at(blo, bhi, c);
-    uint16_t* row = ta + (((size_t)o * NA + xi) * 2) * NA + xj;
-    row[0] = (uint16_t)d1;
-    row[NA] = (uint16_t)((pa == b && a == pb) ? d2 + 1u : kSplitInf);
+    uint16_t* row = ta + (((size_t)o * NA + xi) * 2) * NA + xj0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      uint32_t e2 = d2, e1 = d1, qa = pa, qb = pb;
+#pragma unroll
+      for (int t = W::kSharedA; t < c; ++t) {
+        const uint32_t a = pixel_at(alo, ahi, t), b = pixel_at(blo[v], bhi[v], t);
+        uint32_t cur = e1 + S[a * 16 + b];
+        if (t >= 1 && qa == b && a == qb) cur = min(cur, e2 + 1u);
+        e2 = e1; e1 = cur; qa = a; qb = b;
+      }
+      const uint32_t a = pixel_at(alo, ahi, c), b = pixel_at(blo[v], bhi[v], c);
+      row[BL::dep(v)] = (uint16_t)e1;
+      row[NA + BL::dep(v)] = (uint16_t)((qa == b && a == qb) ? e2 + 1u : kSplitInf);
+    }
   } else {
-    constexpr uint32_t NB = 1u << BB::count;
-    if (idx >= NB * NB) return;
-    const uint32_t yi = idx >> BB::count, yj = idx & (NB - 1u);
+    constexpr uint32_t NB = 1u << BB::count, early = BB::ext(W::kEarlyB);
+    using BE = Bits<early>;
+    using BR = Bits<~early & (NB - 1u)>;
+    static_assert(BE::count == 2, "two early bits");
+    if (idx >= NB * NB / 4) return;
+    const uint32_t yi = idx / (NB / 4), yj0 = BR::dep(idx % (NB / 4));
     load_pixels<MODE>(o, BB::dep(yi), alo, ahi);
-    load_pixels<MODE>(o, BB::dep(yj), blo, bhi);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) load_pixels<MODE>(o, BB::dep(yj0 | BE::dep(v)), blo[v], bhi[v]);
     uint32_t f1 = 0, f2 = 0, na = 0, nb = 0;   // F_{t+1}, F_{t+2}, pixels t+1
 #pragma unroll
-    for (int t = n - 1; t >= c; --t) {
-      const uint32_t a = pixel_at(alo, ahi, t), b = pixel_at(blo, bhi, t);
+    for (int t = n - 1; t >= W::kSharedB; --t) {
+      const uint32_t a = pixel_at(alo, ahi, t), b = pixel_at(blo[0], bhi[0], t);
       uint32_t cur = f1 + S[a * 16 + b];
       if (t + 1 < n && a == nb && na == b) cur = min(cur, f2 + 1u);
       f2 = f1; f1 = cur; na = a; nb = b;
     }
-    tb[((size_t)o * NB + yi) * NB + yj] = f1 | (f2 << 16);
+    uint32_t* row = tb + ((size_t)o * NB + yi) * NB + yj0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      uint32_t g1 = f1, g2 = f2, ma = na, mb = nb;
+#pragma unroll
+      for (int t = W::kSharedB - 1; t >= c; --t) {
+        const uint32_t a = pixel_at(alo, ahi, t), b = pixel_at(blo[v], bhi[v], t);
+        uint32_t cur = g1 + S[a * 16 + b];
+        if (t + 1 < n && a == mb && ma == b) cur = min(cur, g2 + 1u);
+        g2 = g1; g1 = cur; ma = a; mb = b;
+      }
+      row[BE::dep(v)] = g1 | (g2 << 16);
+    }
   }
 }
 
@@ -605,10 +679,12 @@ __global__ void __launch_bounds__(256)
 split_prologue(const __grid_constant__ Lut lut, uint16_t* __restrict__ ta,
                uint32_t* __restrict__ tb) {
   __shared__ uint8_t S[256];
+  launch_dependents();
   S[threadIdx.x] = lut.s[threadIdx.x];
   __syncthreads();
   const int o = blockIdx.z, which = blockIdx.y;
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
+  grid_dependency_wait();   // the pixel strings
   if (MODE == IIV_MODE_HGR && o == 1)
     split_tabulate<MODE, SplitDims<MODE>::kWins - 1>(S, o, which, idx, ta, tb);
   else
@@ -629,20 +705,25 @@ __device__ __forceinline__ void split_rows(int o, const uint16_t* __restrict__ t
   constexpr uint32_t NA = 1u << BA::count, NB = 1u << BB::count;
   constexpr int kThreadsPerRow = NA / 8, kRows = kSplitThreads / kThreadsPerRow;
 
-  const uint32_t i = row_begin + blockIdx.x * kRows + threadIdx.x / kThreadsPerRow;
+  constexpr uint32_t kGroups = (1u << BO::count) / kSplitEpt;   // threads sharing (i, octet)
+  static_assert(kGroups * kSplitEpt == (1u << BO::count), "EPT divides the outside values");
+  const uint32_t e0 = (blockIdx.x % kGroups) * kSplitEpt;
+  const uint32_t i = row_begin + (blockIdx.x / kGroups) * kRows + threadIdx.x / kThreadsPerRow;
   if (i >= row_end) return;
   const uint32_t xj = (threadIdx.x % kThreadsPerRow) * 8;   // A index of the octet's first j
   const uint32_t jb = BA::dep(xj);                          // that j, outside bits zero
   const uint16_t* arow = ta + (((size_t)o * NA + BA::ext(i)) * 2) * NA + xj;
+  grid_dependency_wait();   // the A / B tables
   const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(arow));
   const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(arow + NA));
-  const uint32_t* brow = tb + ((size_t)o * NB + BB::ext(i)) * NB + BB::ext(jb);
-  const size_t at = ((size_t)o << (2 * M::kBits)) + ((size_t)i << M::kBits) + jb;
-  const int below = (int)i - (int)jb;   // entries j < i of the octet at jb + J: below - J
+  const uint32_t J0 = BO::dep(e0);
+  const uint32_t* brow = tb + ((size_t)o * NB + BB::ext(i)) * NB + BB::ext(jb | J0);
+  const size_t at = ((size_t)o << (2 * M::kBits)) + ((size_t)i << M::kBits) + (jb | J0);
+  const int below = (int)i - (int)(jb | J0);   // entries j < i of the octet at J: below - J
 
 #pragma unroll
-  for (uint32_t e = 0; e < (1u << BO::count); ++e) {
-    const uint32_t J = BO::dep(e);   // compile-time after unrolling
+  for (uint32_t e = 0; e < (uint32_t)kSplitEpt; ++e) {
+    const uint32_t J = BO::dep(e);   // compile-time after unrolling (e0's bits lie above)
     uint4 v;
     if (TRI && below - (int)J <= 0) {
       v = make_uint4(0, 0, 0, 0);
@@ -675,7 +756,7 @@ __device__ __forceinline__ void split_rows(int o, const uint16_t* __restrict__ t
 }
 
 template <int MODE, bool TRI, bool MULTI>
-__global__ void __launch_bounds__(kSplitThreads)
+__global__ void __launch_bounds__(kSplitThreads, IIV_SPLIT_MIN_BLOCKS)
 split_kernel(const uint16_t* __restrict__ ta, const uint32_t* __restrict__ tb,
              const __grid_constant__ Dests dests, uint32_t row_begin, uint32_t row_end) {
   const int o = blockIdx.y;
@@ -726,18 +807,28 @@ int generate_split(const Lut& lut, const Dests& dests, uint32_t row_begin, uint3
   uint16_t* ta = reinterpret_cast<uint16_t*>(scratch);
   uint32_t* tb = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + bytes_a);
   constexpr uint32_t pairs = 1u << (2 * (D::kA > D::kB ? D::kA : D::kB));
-  split_prologue<MODE><<<dim3(pairs / 256, 2, M::kOffsets), 256, 0, st>>>(lut, ta, tb);
   constexpr int rows_per_block = kSplitThreads / ((1 << D::kA) / 8);
-  dim3 grid((row_end - row_begin + rows_per_block - 1) / rows_per_block, M::kOffsets);
-  if (tri && multi)
-    split_kernel<MODE, true, true><<<grid, kSplitThreads, 0, st>>>(ta, tb, dests, row_begin, row_end);
-  else if (tri)
-    split_kernel<MODE, true, false><<<grid, kSplitThreads, 0, st>>>(ta, tb, dests, row_begin, row_end);
-  else if (multi)
-    split_kernel<MODE, false, true><<<grid, kSplitThreads, 0, st>>>(ta, tb, dests, row_begin, row_end);
-  else
-    split_kernel<MODE, false, false><<<grid, kSplitThreads, 0, st>>>(ta, tb, dests, row_begin, row_end);
-  const cudaError_t launched = cudaGetLastError();
+  constexpr int groups = (1 << (M::kBits - D::kA)) / kSplitEpt;
+  const dim3 grid((row_end - row_begin + rows_per_block - 1) / rows_per_block * groups,
+                  M::kOffsets);
+  const dim3 block(kSplitThreads);
+  // Both launches are programmatic dependents of the one before (pixel strings -> A / B
+  // tables -> generator): a launch's latency and its blocks' preamble hide behind its
+  // predecessor.  (One prologue + generator pair per offset, so that offset o + 1's tables are
+  // made while offset o's rows drain, measured 3-8 % SLOWER: the second prologue is
+  // latency-bound and the generator cannot start before it ends.)
+  cudaError_t launched = pdl_launch(split_prologue<MODE>, dim3(pairs / 4 / 256, 2, M::kOffsets),
+                                    dim3(256), st, lut, ta, tb);
+  if (launched == cudaSuccess) {
+    if (tri && multi)
+      launched = pdl_launch(split_kernel<MODE, true, true>, grid, block, st, ta, tb, dests, row_begin, row_end);
+    else if (tri)
+      launched = pdl_launch(split_kernel<MODE, true, false>, grid, block, st, ta, tb, dests, row_begin, row_end);
+    else if (multi)
+      launched = pdl_launch(split_kernel<MODE, false, true>, grid, block, st, ta, tb, dests, row_begin, row_end);
+    else
+      launched = pdl_launch(split_kernel<MODE, false, false>, grid, block, st, ta, tb, dests, row_begin, row_end);
+  }
   const cudaError_t freed = cudaFreeAsync(scratch, st);
   if (launched != cudaSuccess) return cuda_fail(launched, "split_kernel");
   if (freed != cudaSuccess) return cuda_fail(freed, "cudaFreeAsync");
