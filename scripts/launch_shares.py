@@ -23,12 +23,13 @@ def main():
     for name in sorted(tot, key=tot.get, reverse=True)[:16]:
         print("%-64s %5d %12.1f us %5.1f%%" % (name[-64:], cnt[name], tot[name],
                                                100.0 * tot[name] / total))
-    pair = {k: v for k, v in tot.items() if "tree_kernel<0, 0, 0>" in k or "pixel_prologue<0>" in k}
-    if len(pair) == 2:
-        t = [v / cnt[k] for k, v in pair.items() if "tree_kernel" in k][0]
-        p = [v / cnt[k] for k, v in pair.items() if "pixel_prologue" in k][0]
-        print("headline step = pixel_prologue<0> + tree_kernel<0,0,0>: %.1f us + %.1f us per launch; "
-              "tree_kernel share %.1f%%" % (p, t, 100.0 * t / (t + p)))
+    step = {k: tot[k] / cnt[k] for k in tot
+            if any(n in k for n in ("split_kernel<0, 0, 0>", "split_prologue<0>", "pixel_prologue<0>"))}
+    if len(step) == 3:
+        t = [v for k, v in step.items() if "split_kernel" in k][0]
+        print("headline step = " + " + ".join("%s %.1f us" % (k.split("::")[-1], v)
+                                              for k, v in sorted(step.items(), key=lambda kv: kv[1]))
+              + " per launch; split_kernel share %.1f%%" % (100.0 * t / sum(step.values())))
 
 
 if __name__ == "__main__":
