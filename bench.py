@@ -292,14 +292,17 @@ def _trace(info):
             "cycles_wait_mt_applier": int(cyc[7])}
 
 
-def phase_a_figures(torch, ops, table):
+def phase_a_figures(torch, ops, table, lut):
     """Scoring prologue of Video._index_changes (video.py:109-116) batched over DISTINCT
-    frames: one iiv_score_frames launch packs every target, scores both banks against the
-    previous frame's bitmap and folds the priorities."""
+    frames: one launch packs every target, scores both banks against the previous frame's
+    bitmap and folds the priorities.  Two ways to the same bits: iiv_score_frames_factored
+    (edit-distance entries evaluated from factor tables in shared memory -- the figure
+    quoted) and iiv_score_frames (entries gathered from the 512 MiB table in HBM)."""
     from iivision_b200 import synth
     nb = int(os.environ.get("IIV_BENCH_SCORE_FRAMES", "1024"))
+    factors = ops.score_factors("DHGR", lut)
 
-    def timed(fraction):
+    def timed(fraction, **dist):
         fr = synth.synthetic_frames("DHGR", nb + 1, fraction, seed=1)
         d = torch.from_numpy(fr).cuda()
         src = ops.pack("DHGR", d[:nb, 0].contiguous(), d[:nb, 1].contiguous())
@@ -307,64 +310,94 @@ def phase_a_figures(torch, ops, table):
         prio = torch.zeros((nb, 2, 32, 256), dtype=torch.int32, device="cuda")
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         for _ in range(3):
-            ops.score_frames("DHGR", src, tgt, table, priority=prio)
+            ops.score_frames("DHGR", src, tgt, priority=prio, **dist)
         torch.cuda.synchronize()
         reps = 20
         ev[0].record()
         for _ in range(reps):
-            ops.score_frames("DHGR", src, tgt, table, priority=prio)
+            ops.score_frames("DHGR", src, tgt, priority=prio, **dist)
         ev[1].record()
         torch.cuda.synchronize()
         return ev[0].elapsed_time(ev[1]) / reps
 
-    ms = timed(1.0)
-    ms_5pct = timed(0.05)
+    def same_bits():
+        fr = synth.synthetic_frames("DHGR", 65, 1.0, seed=2)
+        d = torch.from_numpy(fr).cuda()
+        src = ops.pack("DHGR", d[:64, 0].contiguous(), d[:64, 1].contiguous())
+        pa = torch.full((64, 2, 32, 256), 7, dtype=torch.int32, device="cuda")
+        pb = pa.clone()
+        ta, da = ops.score_frames("DHGR", src, d[1:].contiguous(), table=table, priority=pa)
+        tb, db = ops.score_frames("DHGR", src, d[1:].contiguous(), factors=factors, priority=pb)
+        return bool(torch.equal(ta, tb) and torch.equal(da, db) and torch.equal(pa, pb))
+
+    ms_table = timed(1.0, table=table)
+    ms_table_5pct = timed(0.05, table=table)
+    ms = timed(1.0, factors=factors)
+    ms_5pct = timed(0.05, factors=factors)
     peaks, peak_src = measured_peaks()
     # one diff_weights bank call = 2 x 32 KiB packed in + 32 KiB int32 out +
     # 8192 x 2 B of table = 112 KiB algorithmic, 8192 x 32 B = 256 KiB of sectors; a DHGR
-    # frame is two bank calls.  What the fused launch really streams per frame on top of the
-    # gathers: 16 KiB screen bytes + 32 KiB source in, 32 KiB packed target + 64 KiB diff
-    # out, 64 KiB priorities in and out.
+    # frame is two bank calls.  What a fused launch really streams per frame: 16 KiB screen
+    # bytes + 32 KiB source in, 32 KiB packed target + 64 KiB diff out, 64 KiB priorities in
+    # and out (the factored kernel reads screen bytes and source once per bank: + 48 KiB).
     alg = 2 * 112 * 1024 * nb
     sector = 2 * 8192 * 32 * nb
     streamed = (16 + 32 + 32 + 64 + 128) * 1024 * nb
+    streamed_factored = streamed + (16 + 32) * 1024 * nb
     achieved = alg / (ms * 1e-3) / 1e9
-    # DRAM bytes of one launch of 1024 noise frames from the committed ncu capture
-    # (profiles/r02a_score_frames_ncu_summary.txt: dram__bytes_read 1.8425 GB +
-    # dram__bytes_write 0.1609 GB): 93 B cross the DRAM pins per 2-byte gather
-    traffic = (1.842528e9 + 0.160930e9) * nb / 1024
+    achieved_table = alg / (ms_table * 1e-3) / 1e9
+    # DRAM bytes of one launch of 1024 noise frames from the committed ncu captures
+    traffic_table = (1.842528e9 + 0.160930e9) * nb / 1024
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "score_factored_traffic.json")) as f:
+            traffic = float(json.load(f)["traffic_bytes_per_launch"]) * nb / 1024
+    except (OSError, ValueError, KeyError):
+        pass
     return {
         "scored_frames_per_s": nb / (ms * 1e-3),
         "scored_frames_per_s_5pct_change": nb / (ms_5pct * 1e-3),
-        "scored_5pct_note": "same launch on frames that re-draw 5 % of the bytes of their "
-                            "predecessor (synth fraction 0.05) instead of all of them: the "
-                            "unchanged bytes gather from the tables' diagonals",
+        "scored_frames_per_s_table_gathers": nb / (ms_table * 1e-3),
+        "scored_frames_per_s_table_gathers_5pct_change": nb / (ms_table_5pct * 1e-3),
+        "factored_equals_table_path": same_bits(),
+        "scored_5pct_note": "same launches on frames that re-draw 5 % of the bytes of their "
+                            "predecessor (synth fraction 0.05) instead of all of them: with the "
+                            "table, unchanged bytes gather from its diagonal (cache hits); the "
+                            "factored kernel does the same work whatever the frame shows",
         "scored_frames_note": (
-            "iiv_score_frames: pack + diff_weights (main+aux) + hole mask + priority fold of "
-            "%d DISTINCT DHGR frames per launch (source = the previous frame), device "
-            "resident; %.1f MB streamed per launch (> L2) + %d random table gathers" % (
-                nb, streamed / 1e6, 2 * 8192 * nb)),
+            "iiv_score_frames_factored: pack + diff_weights (main+aux) + hole mask + priority "
+            "fold of %d DISTINCT DHGR frames per launch (source = the previous frame), device "
+            "resident; every edit-distance entry evaluated from factor tables in shared memory "
+            "(208 KiB per SM, 416 KiB in all, built from the LUT in 20 us), no table in HBM; "
+            "%.1f MB streamed per launch (> L2).  scored_frames_per_s_table_gathers: "
+            "iiv_score_frames, the same outputs from %d random gathers into the 512 MiB table; "
+            "outputs compared in the run" % (nb, streamed_factored / 1e6, 2 * 8192 * nb)),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                      "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                     "traffic_gbs": traffic / (ms * 1e-3) / 1e9,
-                     "traffic_frac_of_peak": traffic / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "gathers_per_s": 2 * 8192 * nb / (ms * 1e-3),
-                     "bare_gather_ceiling_per_s": 57.8e9,
-                     "peak_source": peak_src, "kernel": "score_frames_kernel",
+                     "peak_source": peak_src, "kernel": "score_frames_factored_kernel",
                      "kernel_ms": ms, "algorithmic_bytes_per_launch": alg,
-                     "gather_sector_bytes_per_launch": sector,
-                     "streamed_bytes_per_launch": streamed,
-                     "sector_plus_streamed_gbs": (sector + streamed) / (ms * 1e-3) / 1e9,
+                     "streamed_bytes_per_launch": streamed_factored,
+                     "streamed_gbs": streamed_factored / (ms * 1e-3) / 1e9,
+                     "lookups_per_s": 2 * 8192 * nb / (ms * 1e-3),
+                     "table_gather_kernel": {
+                         "kernel": "score_frames_kernel", "kernel_ms": ms_table,
+                         "achieved": achieved_table, "frac": achieved_table / peaks["hbm_gbs"],
+                         "traffic": traffic_table,
+                         "traffic_frac_of_peak": traffic_table / (ms_table * 1e-3) / 1e9
+                         / peaks["hbm_gbs"],
+                         "gathers_per_s": 2 * 8192 * nb / (ms_table * 1e-3),
+                         "bare_gather_ceiling_per_s": 57.8e9,
+                         "gather_sector_bytes_per_launch": sector,
+                         "streamed_bytes_per_launch": streamed},
                      "note": "algorithmic = 112 KiB per bank call (SURVEY 8(d)) x 2 banks x "
-                             "frames; the gathers are uniform over the 512 MiB table (noise "
-                             "frames: the worst case), each a 32 B sector of L2 traffic and, "
-                             "measured, 93 B of DRAM traffic (traffic = dram bytes of the "
-                             "committed ncu capture scaled to this launch).  By DRAM bytes "
-                             "the kernel runs at traffic_frac_of_peak of the copy peak, and at "
-                             "gathers_per_s against the 57.8 G/s of a bare 16-per-thread "
-                             "random-gather loop over the same table "
-                             "(profiles/r02_gather_flavours.txt): DRAM row activations, not "
-                             "bytes, bound it"},
+                             "frames, table bytes included although the factored kernel reads "
+                             "none.  The table-gather kernel is bound by DRAM row activations "
+                             "(93 B of DRAM traffic per 2-byte gather, traffic_frac_of_peak of "
+                             "the copy peak, gathers_per_s against the 57.8 G/s of a bare "
+                             "gather loop, profiles/r02_gather_flavours.txt); the factored "
+                             "kernel replaces a gather by 5 shared-memory loads + ~50 "
+                             "instructions and is bound by issue slots and shared-memory bank "
+                             "conflicts, with its streams (streamed_gbs) on top"},
     }
 
 
@@ -454,7 +487,7 @@ def scorer_figures(torch, ops, single=True, world=1, rank=0, dist=None):
     out["config4_batch_clips"] = batch_clips_figures(torch, ops, table, world, rank, dist)
     if not single:
         return out
-    out.update(phase_a_figures(torch, ops, table))
+    out.update(phase_a_figures(torch, ops, table, lut))
 
     def encode_run(n_clips, n_frames, reps=5):
         clips = np.stack([synth.synthetic_frames("DHGR", n_frames, 1.0, seed=100 + c)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libiivision_b200.so")
 SOURCES = ["iiv_core.cu", "iiv_lut.cu", "iiv_tables.cu", "iiv_scorer.cu",
-           "iiv_encoder.cu", "iiv_stream.cu", "iiv_deflate.cu"]
+           "iiv_encoder.cu", "iiv_stream.cu", "iiv_deflate.cu", "iiv_factored.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
           "-Xcompiler", "-Wall"]

@@ -63,6 +63,13 @@ PROTOTYPES = {
     "iiv_score_frames": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_void_p]),
+    "iiv_score_factors_bytes": (c_size_t, [c_int]),
+    "iiv_score_factors": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
+    "iiv_score_frames_factored": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_void_p,
+                                          c_size_t, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int, c_void_p]),
+    "iiv_score_factor_segments": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
     "iiv_diff_weights_page": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int,
                                       c_void_p, c_void_p, c_int, c_void_p]),
     "iiv_compute_delta_page": (c_int, [c_int, c_int, c_void_p, c_int, c_int,

@@ -356,9 +356,30 @@ def diff_weights(mode, is_aux, source_packed: torch.Tensor,
     return out
 
 
+def score_factors(mode, lut) -> torch.Tensor:
+    """The factor tables iiv_score_frames_factored evaluates edit-distance entries from
+    (uint8 blob, 104 / 106 KiB per byte offset), built from the same 16x16 substitution
+    costs as the table."""
+    _require_cuda()
+    m = mode_id(mode)
+    out = torch.empty((lib.iiv_score_factors_bytes(m),), dtype=torch.uint8, device="cuda")
+    lut = _lut_arg(lut)
+    check(lib.iiv_score_factors(m, lut.ctypes.data, _ptr(out), _stream()))
+    return out
+
+
+def score_factor_segments(mode, offset: int):
+    """[(p, q, mask)]: the pixel segments of the factored chain and their bit windows."""
+    n = ctypes.c_int()
+    p, q, masks = (ctypes.c_int * 16)(), (ctypes.c_int * 16)(), (ctypes.c_uint32 * 16)()
+    check(lib.iiv_score_factor_segments(mode_id(mode), int(offset), ctypes.byref(n), p, q, masks))
+    return [(p[k], q[k], masks[k]) for k in range(n.value)]
+
+
 def score_frames(mode, source_packed: torch.Tensor, target_mem: torch.Tensor,
-                 table: torch.Tensor, priority: torch.Tensor = None,
-                 zero_holes: bool = True, want_packed: bool = True, want_diff: bool = True):
+                 table: torch.Tensor = None, priority: torch.Tensor = None,
+                 zero_holes: bool = True, want_packed: bool = True, want_diff: bool = True,
+                 factors: torch.Tensor = None):
     """The scoring prologue of Video._index_changes (video.py:109-116) for a batch of
     frames in one launch: pack every target, diff_weights of every bank against the
     source bitmap(s), holes zeroed, priorities folded in place.
@@ -366,7 +387,13 @@ def score_frames(mode, source_packed: torch.Tensor, target_mem: torch.Tensor,
     source_packed int64[batch, 32, 128] or [32, 128] (one source for all frames);
     target_mem uint8[batch, banks, 32, 256]; priority int32[batch, banks, 32, 256] or
     None.  Returns (target_packed int64[batch, 32, 128] | None, diff int32[batch, banks,
-    32, 256] | None)."""
+    32, 256] | None).
+
+    The distances come from ``table`` (Bitmap.edit_distances' table, gathered from HBM) or
+    from ``factors`` (score_factors(): evaluated from shared memory, no table needed);
+    the results are bit-identical."""
+    if (table is None) == (factors is None):
+        raise ValueError("pass exactly one of table / factors")
     m = mode_id(mode)
     banks = 2 if m == MODE_DHGR else 1
     batch = target_mem.shape[0]
@@ -387,9 +414,11 @@ def score_frames(mode, source_packed: torch.Tensor, target_mem: torch.Tensor,
     diff = (torch.empty((batch, banks, 32, 256), dtype=torch.int32, device=dev)
             if want_diff else None)
     base = _ptr(target_mem)
-    check(lib.iiv_score_frames(
+    fn, dist = ((lib.iiv_score_frames, table) if factors is None
+                else (lib.iiv_score_frames_factored, factors))
+    check(fn(
         m, _ptr(source_packed), stride, base, (base + 8192) if banks == 2 else None,
-        banks * 8192, _ptr(table), _ptr(tpacked) if want_packed else None,
+        banks * 8192, _ptr(dist), _ptr(tpacked) if want_packed else None,
         _ptr(diff) if want_diff else None, _ptr(priority) if priority is not None else None,
         int(bool(zero_holes)), batch, _stream()))
     return tpacked, diff

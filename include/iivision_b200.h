@@ -230,6 +230,30 @@ int iiv_score_frames(int mode, const uint64_t* d_source_packed, size_t source_st
                      uint64_t* d_target_packed, int32_t* d_diff, int32_t* d_priority,
                      int zero_holes, int batch, void* stream);
 
+/* iiv_score_frames without the table.  An edit-distance entry (make_data_tables.py:92-108)
+ * is a product of per-pixel 2x2 (min,+) matrices; the product over a segment of pixels is a
+ * function of a 4-6 bit window of each masked value, so the entry can be evaluated from small
+ * per-segment FACTOR tables (104 / 106 KiB per byte offset: a bank's two offsets live in one
+ * SM's shared memory) instead of gathered from the 512 MiB / 1 GiB table in HBM.
+ *   iiv_score_factors_bytes   size of the factor tables of a mode (all byte offsets)
+ *   iiv_score_factors         fills d_factors (16-byte aligned) from the 16x16 substitution
+ *                             costs compute_substitute_costs gives (make_data_tables.py:73-89);
+ *                             the same h_lut as iiv_table_generate
+ *   iiv_score_frames_factored iiv_score_frames with d_factors in the place of d_table; every
+ *                             output is bit-identical
+ *   iiv_score_factor_segments host-only: the segments [p[k], q[k]) of pixels and the bit
+ *                             window masks[k] feeding pixels p[k]..min(q[k], n-1) at `offset`
+ *                             (arrays of 16), for the CPU tests */
+size_t iiv_score_factors_bytes(int mode);
+int iiv_score_factors(int mode, const int32_t* h_lut, uint8_t* d_factors, void* stream);
+int iiv_score_frames_factored(int mode, const uint64_t* d_source_packed, size_t source_stride,
+                              const uint8_t* d_target_main, const uint8_t* d_target_aux,
+                              size_t mem_stride, const uint8_t* d_factors,
+                              uint64_t* d_target_packed, int32_t* d_diff, int32_t* d_priority,
+                              int zero_holes, int batch, void* stream);
+int iiv_score_factor_segments(int mode, int offset, int* n_segments, int* p, int* q,
+                              uint32_t* masks);
+
 /* Bitmap._diff_weights_page (screen.py:453-494) on n_rows rows of 128 words:
  * d_out int32[n_rows][256]. */
 int iiv_diff_weights_page(int mode, int is_aux, const uint64_t* d_source_rows,

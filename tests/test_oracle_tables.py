@@ -202,3 +202,45 @@ def test_split_windows(mode):
         _lib.check(_lib.lib.iiv_table_split_windows(0, 2, ctypes.byref(ctypes.c_int()),
                                                     ctypes.byref(ctypes.c_uint32()),
                                                     ctypes.byref(ctypes.c_uint32())))
+
+
+@pytest.mark.parametrize("mode", ["HGR", "DHGR"])
+def test_factor_segments(mode):
+    """The structural facts the factored scorer (csrc/iiv_factored.cu) relies on: its pixel
+    segments tile 0..n, and pixels p..min(q, n-1) of a value's string are functions of the
+    segment's bit window only -- against the oracle's pixel strings.  Also that the
+    segment-by-segment (min,+) product equals the oracle's chain on random pairs."""
+    import ctypes
+    from iivision_b200 import _lib
+    pix = tables.all_pixel_strings(mode).astype(np.int64)
+    bits, n = tables.MASKED_BITS[mode], tables.MASKED_DOTS[mode]
+    v = np.arange(1 << bits)
+    rng = np.random.default_rng(5)
+    lut = tables.substitution_lut(0).astype(np.int64)
+    for o in range(pix.shape[0]):
+        cnt = ctypes.c_int()
+        p, q, m = (ctypes.c_int * 16)(), (ctypes.c_int * 16)(), (ctypes.c_uint32 * 16)()
+        _lib.check(_lib.lib.iiv_score_factor_segments(tables.MODES[mode], o, ctypes.byref(cnt),
+                                                      p, q, m))
+        segs = [(p[k], q[k], m[k]) for k in range(cnt.value)]
+        assert segs[0][0] == 0 and segs[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(segs[:-1], segs[1:]))
+        room = 0
+        for k, (sp, sq, mask) in enumerate(segs):
+            hi = min(sq, n - 1)
+            assert np.array_equal(pix[o][v, sp:hi + 1], pix[o][v & mask, sp:hi + 1]), (mode, o, k)
+            room += (4 if k in (0, len(segs) - 1) else 8) << (2 * bin(mask).count("1"))
+        assert 2 * room <= 227 * 1024          # a bank's two offsets in one SM's shared memory
+        assert room * pix.shape[0] == _lib.lib.iiv_score_factors_bytes(tables.MODES[mode])
+        i, j = rng.integers(0, 1 << bits, 2000), rng.integers(0, 1 << bits, 2000)
+        want = np.array([tables.chain_distance(pix[o][a], pix[o][b], lut) for a, b in zip(i, j)])
+        f1, f2 = np.zeros(2000, np.int64), np.full(2000, 0x4000, np.int64)
+        for sp, sq, mask in reversed(segs):
+            a, b = pix[o][i & mask], pix[o][j & mask]
+            for t in range(sq - 1, sp - 1, -1):
+                cur = f1 + lut[a[:, t], b[:, t]]
+                if t + 1 < n:
+                    sw = (a[:, t] == b[:, t + 1]) & (a[:, t + 1] == b[:, t])
+                    cur = np.where(sw, np.minimum(cur, f2 + 1), cur)
+                f2, f1 = f1, cur
+        assert np.array_equal(f1, want), (mode, o)
