@@ -10,4 +10,5 @@ python bench.py > gpurun_out/r02h_bench.json 2> gpurun_out/r02h_bench.err; tail 
 IIV_BENCH_LONG_FRAMES=60 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/r02h_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r02h_ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:split_kernel -s 3 -c 1 -o gpurun_out/r02h_prof_split python bench.py --steps 2 --warmup 1 --no-scorer --no-cpu-baseline > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:split_prologue -s 3 -c 1 -o gpurun_out/r02h_prof_split_prologue python bench.py --steps 2 --warmup 1 --no-scorer --no-cpu-baseline > /dev/null 2>&1
+IIV_BENCH_LONG_FRAMES=60 ncu --set full --clock-control none --import-source on -k regex:score_frames_factored -s 3 -c 1 -o gpurun_out/r02h_prof_factored python bench.py --scorer-only > /dev/null 2>&1
 ls -la gpurun_out | tail -8
