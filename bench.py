@@ -474,6 +474,38 @@ def batch_clips_figures(torch, ops, table, world=1, rank=0, dist=None):
                     "slowest rank's median CUDA-event time of 5 launches"}
 
 
+def sharded_scoring_figures(torch, ops, lut, world, rank, dist):
+    """Scored frames/s at N GPUs: frames are independent, so every rank scores its own 1 024
+    distinct frames (its own factor tables, no collective); the figure is all frames over the
+    slowest rank's time."""
+    from iivision_b200 import synth
+    nb = int(os.environ.get("IIV_BENCH_SCORE_FRAMES", "1024"))
+    factors = ops.score_factors("DHGR", lut)
+    fr = synth.synthetic_frames("DHGR", nb + 1, 1.0, seed=1 + 1000 * rank)
+    d = torch.from_numpy(fr).cuda()
+    src = ops.pack("DHGR", d[:nb, 0].contiguous(), d[:nb, 1].contiguous())
+    tgt = d[1:].contiguous()
+    prio = torch.zeros((nb, 2, 32, 256), dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        ops.score_frames("DHGR", src, tgt, priority=prio, factors=factors)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    reps = 20
+    ev[0].record()
+    for _ in range(reps):
+        ops.score_frames("DHGR", src, tgt, priority=prio, factors=factors)
+    ev[1].record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]) / reps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"scored_frames_per_s": world * nb / (ms * 1e-3), "frames_per_gpu": nb,
+            "ms_slowest_rank": ms, "n_gpus": world, "scaling": "weak",
+            "note": "iiv_score_frames_factored on %d distinct DHGR frames per rank (frames "
+                    "sharded, no collective); all frames / slowest rank's CUDA-event time" % nb}
+
+
 def scorer_figures(torch, ops, single=True, world=1, rank=0, dist=None):
     """Second hot path, DHGR NTSC, on DISTINCT synthetic data everywhere: (a) the scoring
     prologue batched over frames, (b) bit-exact encoding of independent clips, one block
@@ -486,6 +518,7 @@ def scorer_figures(torch, ops, single=True, world=1, rank=0, dist=None):
     out = {}
     out["config4_batch_clips"] = batch_clips_figures(torch, ops, table, world, rank, dist)
     if not single:
+        out["scored_frames"] = sharded_scoring_figures(torch, ops, lut, world, rank, dist)
         return out
     out.update(phase_a_figures(torch, ops, table, lut))
 
