@@ -195,6 +195,12 @@ __device__ __forceinline__ void tabulate_dispatch(const uint8_t* S, int o, int k
   }
 }
 
+// The blob: the tables of every byte offset, then a 16-byte trailer whose first word says
+// whether the LUT's diagonal is zero -- then entry(x, x) = 0 and the scorer skips the lookup of
+// a window that already shows what the target shows.
+template <int MODE>
+constexpr size_t kBlobBytes = (size_t)Mode<MODE>::kOffsets * kOffsetBytes<MODE> + 16;
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 factor_prologue(const __grid_constant__ Lut lut, unsigned char* __restrict__ factors) {
@@ -203,6 +209,12 @@ factor_prologue(const __grid_constant__ Lut lut, unsigned char* __restrict__ fac
   __syncthreads();
   const int o = blockIdx.z, k = blockIdx.y;
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx == 0 && o == 0 && k == 0) {
+    uint32_t zero = 1;
+    for (int a = 0; a < 16; ++a) zero &= S[a * 17] == 0;
+    *reinterpret_cast<uint4*>(factors + (size_t)Mode<MODE>::kOffsets * kOffsetBytes<MODE>) =
+        make_uint4(zero, 0u, 0u, 0u);
+  }
   unsigned char* tab = factors + (size_t)o * kOffsetBytes<MODE>;
   if (MODE == IIV_MODE_HGR && o == 1)
     tabulate_dispatch<MODE, win_of<MODE>(1)>(S, o, k, idx, tab);
@@ -265,6 +277,8 @@ score_frames_factored_kernel(const uint64_t* __restrict__ src, size_t src_stride
     uint4* s = reinterpret_cast<uint4*>(smem + half * kTab);
     for (uint32_t k = threadIdx.x; k < kTab / 16; k += kFactoredThreads) s[k] = __ldg(g + k);
   }
+  const bool diag0 =
+      *reinterpret_cast<const uint32_t*>(factors + (size_t)M::kOffsets * kTab) != 0u;
   __syncthreads();
 
   const int group = threadIdx.x >> 8, t = threadIdx.x & 255;   // 4 groups of 256 threads
@@ -331,10 +345,11 @@ score_frames_factored_kernel(const uint64_t* __restrict__ src, size_t src_stride
     const int o0 = byte_offset<MODE>(0, bank), o1 = byte_offset<MODE>(1, bank);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      dw[2 * k] = (int32_t)chain_lookup<MODE, 0>(
-          smem, mask_shift<MODE>(sw[k], o0), mask_shift<MODE>(tp[k], o0));
-      dw[2 * k + 1] = (int32_t)chain_lookup<MODE, MODE == IIV_MODE_HGR ? 1 : 0>(
-          smem + kTab, mask_shift<MODE>(sw[k], o1), mask_shift<MODE>(tp[k], o1));
+      const uint32_t x0 = mask_shift<MODE>(sw[k], o0), y0 = mask_shift<MODE>(tp[k], o0);
+      const uint32_t x1 = mask_shift<MODE>(sw[k], o1), y1 = mask_shift<MODE>(tp[k], o1);
+      dw[2 * k] = (diag0 && x0 == y0) ? 0 : (int32_t)chain_lookup<MODE, 0>(smem, x0, y0);
+      dw[2 * k + 1] = (diag0 && x1 == y1) ? 0
+                      : (int32_t)chain_lookup<MODE, MODE == IIV_MODE_HGR ? 1 : 0>(smem + kTab, x1, y1);
     }
     const bool hole = zero_holes && (col == 60 || col == 124);   // offsets 120..127, 248..255
     if (hole) {
@@ -407,9 +422,8 @@ int launch_score(const uint64_t* src, size_t src_stride, const uint8_t* tmain,
 using namespace iiv;
 
 extern "C" size_t iiv_score_factors_bytes(int mode) {
-  if (mode == IIV_MODE_HGR) return (size_t)Mode<IIV_MODE_HGR>::kOffsets * kOffsetBytes<IIV_MODE_HGR>;
-  if (mode == IIV_MODE_DHGR)
-    return (size_t)Mode<IIV_MODE_DHGR>::kOffsets * kOffsetBytes<IIV_MODE_DHGR>;
+  if (mode == IIV_MODE_HGR) return kBlobBytes<IIV_MODE_HGR>;
+  if (mode == IIV_MODE_DHGR) return kBlobBytes<IIV_MODE_DHGR>;
   return 0;
 }
 

@@ -235,7 +235,8 @@ int iiv_score_frames(int mode, const uint64_t* d_source_packed, size_t source_st
  * function of a 4-6 bit window of each masked value, so the entry can be evaluated from small
  * per-segment FACTOR tables (104 / 106 KiB per byte offset: a bank's two offsets live in one
  * SM's shared memory) instead of gathered from the 512 MiB / 1 GiB table in HBM.
- *   iiv_score_factors_bytes   size of the factor tables of a mode (all byte offsets)
+ *   iiv_score_factors_bytes   size of the factor tables of a mode (all byte offsets, plus a
+ *                             16-byte trailer: is the LUT's diagonal zero)
  *   iiv_score_factors         fills d_factors (16-byte aligned) from the 16x16 substitution
  *                             costs compute_substitute_costs gives (make_data_tables.py:73-89);
  *                             the same h_lut as iiv_table_generate

@@ -231,7 +231,7 @@ def test_factor_segments(mode):
             assert np.array_equal(pix[o][v, sp:hi + 1], pix[o][v & mask, sp:hi + 1]), (mode, o, k)
             room += (4 if k in (0, len(segs) - 1) else 8) << (2 * bin(mask).count("1"))
         assert 2 * room <= 227 * 1024          # a bank's two offsets in one SM's shared memory
-        assert room * pix.shape[0] == _lib.lib.iiv_score_factors_bytes(tables.MODES[mode])
+        assert room * pix.shape[0] + 16 == _lib.lib.iiv_score_factors_bytes(tables.MODES[mode])
         i, j = rng.integers(0, 1 << bits, 2000), rng.integers(0, 1 << bits, 2000)
         want = np.array([tables.chain_distance(pix[o][a], pix[o][b], lut) for a, b in zip(i, j)])
         f1, f2 = np.zeros(2000, np.int64), np.full(2000, 0x4000, np.int64)
