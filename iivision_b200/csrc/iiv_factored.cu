@@ -268,18 +268,33 @@ score_frames_factored_kernel(const uint64_t* __restrict__ src, size_t src_stride
   using M = Mode<MODE>;
   constexpr int kBanks = MODE == IIV_MODE_DHGR ? 2 : 1;
   constexpr uint32_t kTab = kOffsetBytes<MODE>;
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t tables_bar;
   const int bank = blockIdx.x % kBanks;   // index into diff / priority: 0 main, 1 aux
+  // The bank's two tables come in as two TMA bulk copies (cp.async.bulk, 104 / 106 KiB each)
+  // that complete on an mbarrier; the block's threads meanwhile fetch the screen bytes, source
+  // words and priorities of their first item and wait only when they need a table entry.
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tables_bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                 "r"(2u * kTab)
+                 : "memory");
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const uint4* g = reinterpret_cast<const uint4*>(
-        factors + (size_t)byte_offset<MODE>(half, bank) * kTab);
-    uint4* s = reinterpret_cast<uint4*>(smem + half * kTab);
-    for (uint32_t k = threadIdx.x; k < kTab / 16; k += kFactoredThreads) s[k] = __ldg(g + k);
+    for (int half = 0; half < 2; ++half) {
+      const unsigned char* g = factors + (size_t)byte_offset<MODE>(half, bank) * kTab;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem + half * kTab);
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(dst), "l"(g), "r"(kTab), "r"(bar)
+          : "memory");
+    }
   }
   const bool diag0 =
       *reinterpret_cast<const uint32_t*>(factors + (size_t)M::kOffsets * kTab) != 0u;
-  __syncthreads();
+  __syncthreads();   // the barrier is initialised before anyone polls it
+  bool tables_ready = false;
 
   const int group = threadIdx.x >> 8, t = threadIdx.x & 255;   // 4 groups of 256 threads
   const int n_items = 4 * batch, stride = (gridDim.x / kBanks) * 4;
@@ -340,6 +355,18 @@ score_frames_factored_kernel(const uint64_t* __restrict__ src, size_t src_stride
       uint64_t* o = tpacked + frame * 4096 + c0;
       *reinterpret_cast<ulonglong2*>(o) = make_ulonglong2(tp[0], tp[1]);
       *reinterpret_cast<ulonglong2*>(o + 2) = make_ulonglong2(tp[2], tp[3]);
+    }
+    if (!tables_ready) {
+      uint32_t done = 0;
+      while (!done)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar)
+            : "memory");
+      tables_ready = true;
     }
     int32_t dw[8];
     const int o0 = byte_offset<MODE>(0, bank), o1 = byte_offset<MODE>(1, bank);
