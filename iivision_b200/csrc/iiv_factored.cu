@@ -102,33 +102,6 @@ static_assert(2 * kOffsetBytes<IIV_MODE_HGR> <= 227 * 1024 &&
                   2 * kOffsetBytes<IIV_MODE_DHGR> <= 227 * 1024,
               "a bank's two byte offsets fit one SM's shared memory");
 
-// Compile-time bit window: ext gathers the window's bits of v into a dense index (lowest bit
-// first), dep scatters an index back; one shift + mask per run of the window.
-__host__ __device__ constexpr int ctz_c(uint32_t x) {
-  int n = 0;
-  while (n < 32 && !((x >> n) & 1u)) ++n;
-  return n;
-}
-template <uint32_t MASK, int OUT = 0>
-struct Ext {
-  static constexpr int lo = ctz_c(MASK);
-  static constexpr int len = ctz_c(~(MASK >> lo));
-  static constexpr uint32_t rest = MASK & ~(((1u << len) - 1u) << lo);
-  static constexpr int count = len + Ext<rest, OUT + len>::count;
-  __host__ __device__ static __forceinline__ constexpr uint32_t ext(uint32_t v) {
-    return (((v >> lo) & ((1u << len) - 1u)) << OUT) | Ext<rest, OUT + len>::ext(v);
-  }
-  __host__ __device__ static __forceinline__ constexpr uint32_t dep(uint32_t x) {
-    return (((x >> OUT) & ((1u << len) - 1u)) << lo) | Ext<rest, OUT + len>::dep(x);
-  }
-};
-template <int OUT>
-struct Ext<0u, OUT> {
-  static constexpr int count = 0;
-  __host__ __device__ static __forceinline__ constexpr uint32_t ext(uint32_t) { return 0u; }
-  __host__ __device__ static __forceinline__ constexpr uint32_t dep(uint32_t) { return 0u; }
-};
-
 template <int MODE, int WIN, int K>
 struct Seg {
   static constexpr SegDesc d = Chain<MODE, WIN>::seg(K);

@@ -536,32 +536,8 @@ constexpr int kSplitThreads = IIV_SPLIT_THREADS;
 constexpr int kSplitEpt = IIV_SPLIT_EPT;   // values of the outside bits one thread walks
 constexpr uint32_t kSplitInf = 0x4000;   // + any F stays below 0x8000 (n * 255 <= 4590)
 
-__host__ __device__ constexpr int ctz_c(uint32_t x) {
-  int n = 0;
-  while (n < 32 && !((x >> n) & 1u)) ++n;
-  return n;
-}
-
-// Compile-time bit window of at most two runs: ext gathers the window's bits of v into a
-// dense index (lowest bit first), dep scatters an index back.
 template <uint32_t MASK>
-struct Bits {
-  static constexpr int lo1 = ctz_c(MASK);
-  static constexpr int len1 = ctz_c(~(MASK >> lo1));
-  static constexpr uint32_t rest = MASK & ~(((1u << len1) - 1u) << lo1);
-  static constexpr int lo2 = rest ? ctz_c(rest) : 0;
-  static constexpr int len2 = rest ? ctz_c(~(rest >> lo2)) : 0;
-  static_assert(rest == (((1u << len2) - 1u) << lo2), "window of at most two runs");
-  static constexpr int count = len1 + len2;
-  __host__ __device__ static __forceinline__ constexpr uint32_t ext(uint32_t v) {
-    return ((v >> lo1) & ((1u << len1) - 1u)) |
-           (len2 ? ((v >> lo2) & ((1u << len2) - 1u)) << len1 : 0u);
-  }
-  __host__ __device__ static __forceinline__ constexpr uint32_t dep(uint32_t x) {
-    return ((x & ((1u << len1) - 1u)) << lo1) |
-           (len2 ? ((x >> len1) & ((1u << len2) - 1u)) << lo2 : 0u);
-  }
-};
+using Bits = Ext<MASK>;   // iiv_common.cuh
 
 // Windows per (mode, window set).  HGR has one set per offset (the palette bit that shifts
 // the body's dots is bit 10 at offset 0 and bit 3 at offset 1); DHGR's dots are the value.
