@@ -1,6 +1,7 @@
 """The reference's OWN unit tests, unmodified, run against this package's modules.
 
-transcoder/colours_test.py, opcodes_test.py and symbol_table_test.py import their subject by
+transcoder/colours_test.py, opcodes_test.py, symbol_table_test.py and frame_grabber_test.py
+import their subject by
 bare module name (``import colours``); here those names are bound to iivision_b200's modules
 of the same name and the test files are loaded from the reference tree where they lie.  These
 are the suites whose subjects need no CUDA device; screen_test.py and video_test.py exercise
@@ -20,7 +21,8 @@ REF = "/root/reference/transcoder"
 pytestmark = [pytest.mark.reference,
               pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")]
 
-ALIASES = ("colours", "palette", "opcodes", "symbol_table", "machine", "video_mode")
+ALIASES = ("colours", "palette", "opcodes", "symbol_table", "machine", "video_mode",
+           "frame_grabber")
 
 
 def _run_reference_suite(filename: str):
@@ -45,7 +47,8 @@ def _run_reference_suite(filename: str):
 
 
 @pytest.mark.parametrize("filename,n_tests", [("colours_test.py", 5), ("opcodes_test.py", 1),
-                                              ("symbol_table_test.py", 1)])
+                                              ("symbol_table_test.py", 1),
+                                              ("frame_grabber_test.py", 1)])
 def test_reference_suite_passes_on_our_modules(filename, n_tests):
     count, result = _run_reference_suite(filename)
     assert count == n_tests
