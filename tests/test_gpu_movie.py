@@ -102,3 +102,43 @@ def test_transcode_device(mods, device_tables, case):
                  field(ops.F_PRIO_MAIN, torch.int32, (32, 256)),
                  field(ops.F_AUX, torch.uint8, (32, 256)),
                  field(ops.F_PRIO_AUX, torch.int32, (32, 256)))
+
+
+def test_movie_from_the_frame_cache(mods, tmp_path):
+    """The same movie with its frames served by frame_grabber.FileFrameGrabber from the
+    reference's on-disk cache of converted frames (frame_grabber.py:73-76, :95-99): the bytes
+    of the reference's Movie.encode + emit_stream."""
+    from iivision_b200 import frame_grabber
+    case = [c for c in CASES if "DHGR" in c.upper()] or CASES
+    g = np.load(os.path.join(GOLDEN, "movie_%s.npz" % case[0]))
+    mode = str(g["mode"])
+    frames, samples = g["frames"], g["audio"]
+    vm = getattr(mods.video_mode.VideoMode, mode)
+    video_file = str(tmp_path / "synthetic.mp4")
+    d = frame_grabber.FileFrameGrabber._output_dir(video_file, vm, mods.palette.Palette.NTSC)
+    os.makedirs(d)
+    for k in range(frames.shape[0]):
+        if mode == "DHGR":
+            frames[k, 0].reshape(8192).tofile("%s/%08d.BIN" % (d, k))
+            frames[k, 1].reshape(8192).tofile("%s/%08d.AUX" % (d, k))
+        else:
+            frames[k, 0].reshape(8192).tofile("%s/%08dC.BIN" % (d, k))
+
+    class Audio:
+        sample_rate = float(g["sample_rate"])
+
+        @staticmethod
+        def audio_stream():
+            yield from (int(a) for a in samples)
+
+    grabber = frame_grabber.FileFrameGrabber(video_file, vm, mods.palette.Palette.NTSC,
+                                             input_frame_rate=float(g["input_frame_rate"]))
+    assert np.array_equal(grabber.frames_array(), frames)
+    random.seed(int(g["rng_seed"]))
+    np.random.seed(int(g["rng_seed"]))
+    m = mods.movie.Movie(video_file, every_n_video_frames=int(g["every_n_video_frames"]),
+                         max_bytes_out=int(g["max_bytes_out"]) or None, video_mode=vm,
+                         palette=mods.palette.Palette.NTSC, audio=Audio(), frame_grabber=grabber)
+    with contextlib.redirect_stdout(io.StringIO()):
+        data = bytes(m.emit_stream(m.encode()))
+    assert np.array_equal(np.frombuffer(data, np.uint8), g["bytes"])
