@@ -77,3 +77,26 @@ def test_factored_bad_arguments(oracle_luts):
     src, tgt_mem, _, _ = _frames("DHGR", 2, 1.0, 1)
     with pytest.raises(ValueError):
         ops.score_frames("DHGR", src, tgt_mem)
+
+
+@pytest.mark.parametrize("mode", ["HGR", "DHGR"])
+def test_asymmetric_luts_keep_their_orientation(mode):
+    """The C ABI takes any 16x16 costs in 0..255, symmetric or not (the reference's are
+    symmetric): S[a][b] with a from the source's string, b from the target's, in the chain
+    kernel, the split generator and the factored scorer alike."""
+    import torch
+    from iivision_b200 import ops
+    from iivision_b200._lib import ALGO_CHAIN, ALGO_SPLIT
+    rng = np.random.default_rng(23)
+    src, tgt_mem, _, _ = _frames(mode, 16, 1.0, 31)
+    for _ in range(2):
+        lut = rng.integers(0, 256, size=(16, 16)).astype(np.int32)
+        lut[rng.random((16, 16)) < 0.2] = 0
+        a = ops.table_generate(mode, lut, algo=ALGO_CHAIN)
+        b = ops.table_generate(mode, lut, algo=ALGO_SPLIT)
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16))
+        del a
+        _, da = ops.score_frames(mode, src, tgt_mem, b)
+        _, db = ops.score_frames(mode, src, tgt_mem, factors=ops.score_factors(mode, lut))
+        assert torch.equal(da, db)
+        del b
