@@ -196,7 +196,32 @@ _pinned_pool = _PinnedPool()
 
 DEFLATE_GROUP = 64      # device blocks (32 KiB each) per piece of load_member's index
 STAGE_SLOTS, STAGE_BYTES = 3, 16 << 20
-_stage = {}
+
+
+class _StageRings:
+    """Rings of page-locked staging slots, one ring per stream on its way home at a time
+    (make_data_tables.main writes several files at once); allocating a ring costs ~10 ms of
+    cudaHostAlloc, so finished rings are kept for the next stream."""
+
+    def __init__(self):
+        import threading
+        self.lock = threading.Lock()
+        self.free = {}
+
+    def take(self, dev):
+        with self.lock:
+            rings = self.free.setdefault(dev, [])
+            if rings:
+                return rings.pop()
+        return [torch.empty(STAGE_BYTES, dtype=torch.uint8, pin_memory=True)
+                for _ in range(STAGE_SLOTS)]
+
+    def give(self, dev, ring):
+        with self.lock:
+            self.free.setdefault(dev, []).append(ring)
+
+
+_rings = _StageRings()
 
 
 def _staged_home(stream: torch.Tensor):
@@ -205,66 +230,83 @@ def _staged_home(stream: torch.Tensor):
     ones are already crossing PCIe.  A yielded buffer is valid until the next is asked for.
     (Page-locking memory for the whole stream would cost more than the copy.)"""
     dev = stream.device
-    if dev not in _stage:
-        _stage[dev] = [torch.empty(STAGE_BYTES, dtype=torch.uint8, pin_memory=True)
-                       for _ in range(STAGE_SLOTS)]
-    slots = _stage[dev]
-    total = stream.numel()
-    n = (total + STAGE_BYTES - 1) // STAGE_BYTES
-    events = [None] * n
+    slots = _rings.take(dev)
+    try:
+        total = stream.numel()
+        n = (total + STAGE_BYTES - 1) // STAGE_BYTES
+        events = [None] * n
 
-    def issue(k):
-        lo = k * STAGE_BYTES
-        hi = min(total, lo + STAGE_BYTES)
-        slots[k % STAGE_SLOTS][:hi - lo].copy_(stream[lo:hi], non_blocking=True)
-        events[k] = torch.cuda.Event()
-        events[k].record()
+        def issue(k):
+            lo = k * STAGE_BYTES
+            hi = min(total, lo + STAGE_BYTES)
+            slots[k % STAGE_SLOTS][:hi - lo].copy_(stream[lo:hi], non_blocking=True)
+            events[k] = torch.cuda.Event()
+            events[k].record()
 
-    for k in range(min(n, STAGE_SLOTS)):
-        issue(k)
-    for k in range(n):
-        events[k].synchronize()
-        hi = min(total, (k + 1) * STAGE_BYTES)
-        yield slots[k % STAGE_SLOTS].numpy()[:hi - k * STAGE_BYTES]
-        if k + STAGE_SLOTS < n:
-            issue(k + STAGE_SLOTS)       # the consumer is done with slot k
+        for k in range(min(n, STAGE_SLOTS)):
+            issue(k)
+        for k in range(n):
+            events[k].synchronize()
+            hi = min(total, (k + 1) * STAGE_BYTES)
+            yield slots[k % STAGE_SLOTS].numpy()[:hi - k * STAGE_BYTES]
+            if k + STAGE_SLOTS < n:
+                issue(k + STAGE_SLOTS)       # the consumer is done with slot k
+    finally:
+        torch.cuda.current_stream().synchronize()
+        _rings.give(dev, slots)
 
 
 def make_edit_distance(pal: Type[palette.BasePalette], edp: EditDistanceParams,
                        bitmap_cls: Type[screen.Bitmap],
-                       nominal_colours: Type[colours.NominalColours] = None):
+                       nominal_colours: Type[colours.NominalColours] = None,
+                       _writer=None):
     """Write file containing (D)HGR edit distance matrix for a palette.
 
     Same container and member as the reference's ``np.savez_compressed(data,
     edit_distance=dist)`` (make_data_tables.py:186-188) -- ``np.load(...)['edit_distance']``
     reads it -- but the table never comes to the host uncompressed: the device deflates it
     where it was generated (ops.deflate_table) and only the compressed stream crosses PCIe,
-    slice by slice, while the slices before it are being written to the file."""
+    slice by slice, while the slices before it are being written to the file.
+
+    ``_writer`` (main()'s): called with the function that brings the stream home and writes
+    the file, instead of that function being run here -- the next table is then generated
+    and deflated while this one is still being written."""
     from . import deflate
     m = _mode_of(bitmap_cls)
     table = compute_edit_distance_device(edp, bitmap_cls, ops.LAYOUT_TRIANGULAR)
     stream, sizes, block_crc, block_bytes = ops.deflate_table(m, table)
-    home = _staged_home(stream)
-    first = next(home)              # starts the copies; the bookkeeping below overlaps them
-    # checksums and the piece index
     shape = tuple(table.shape)
-    like = np.broadcast_to(np.uint16(0), shape)
-    header = npz_io._npy_header(like)
-    body_crc = deflate.crc32_of_equal_parts(block_crc, block_bytes)
-    crc = deflate.crc32_combine(zlib.crc32(header), body_crc, len(block_crc) * block_bytes)
-    group = DEFLATE_GROUP if len(sizes) % DEFLATE_GROUP == 0 else 1
-    ends = np.cumsum(sizes.astype(np.int64))
-    comp_len = ends[group - 1::group] - np.concatenate(([0], ends[group - 1::group][:-1]))
-    comp_off = ends[group - 1::group] - comp_len
-    raw_len = group * block_bytes
-    group_crc = deflate.crc32_of_groups(block_crc, block_bytes, group)
-    pieces = [(k * raw_len, raw_len, int(comp_off[k]), int(comp_len[k]), int(group_crc[k]))
-              for k in range(len(comp_len))]
+    del table                       # deflate_table has synchronised: the stream is complete
     data = "%s/%s_palette_%d_edit_distance.npz" % (
         DATA_DIR, bitmap_cls.NAME, pal.ID.value)
-    import itertools
-    npz_io.savez_predeflated(data, "edit_distance", like, itertools.chain((first,), home),
-                             stream.numel(), crc, pieces)
+
+    def write_file():
+        home = _staged_home(stream)
+        first = next(home)          # starts the copies; the bookkeeping below overlaps them
+        # checksums and the piece index
+        like = np.broadcast_to(np.uint16(0), shape)
+        header = npz_io._npy_header(like)
+        body_crc = deflate.crc32_of_equal_parts(block_crc, block_bytes)
+        crc = deflate.crc32_combine(zlib.crc32(header), body_crc, len(block_crc) * block_bytes)
+        group = DEFLATE_GROUP if len(sizes) % DEFLATE_GROUP == 0 else 1
+        ends = np.cumsum(sizes.astype(np.int64))
+        comp_len = ends[group - 1::group] - np.concatenate(([0], ends[group - 1::group][:-1]))
+        comp_off = ends[group - 1::group] - comp_len
+        raw_len = group * block_bytes
+        group_crc = deflate.crc32_of_groups(block_crc, block_bytes, group)
+        pieces = [(k * raw_len, raw_len, int(comp_off[k]), int(comp_len[k]), int(group_crc[k]))
+                  for k in range(len(comp_len))]
+        import itertools
+        try:
+            npz_io.savez_predeflated(data, "edit_distance", like, itertools.chain((first,), home),
+                                     stream.numel(), crc, pieces)
+        finally:
+            home.close()            # the staging ring goes back whatever happened
+
+    if _writer is None:
+        write_file()
+    else:
+        _writer(write_file)
 
 
 def table_jobs():
@@ -290,13 +332,41 @@ def main(rank: int = None, world: int = None):
         mine = parallel.shard_jobs([j[3] for j in jobs], world, rank)
     edps = {}
     written = []
-    for k in mine:
-        p, bitmap_cls, nominal, _ = jobs[k]
-        if p not in edps:
-            print("Processing palette %s" % p)
-            edps[p] = compute_substitute_costs(p)
-        make_edit_distance(p, edps[p], bitmap_cls, nominal)
-        written.append("%s/%s_palette_%d_edit_distance.npz" % (DATA_DIR, bitmap_cls.NAME, p.ID.value))
+    # A file's way home (PCIe slices + the host's file writes, ~0.1 s) runs on a thread of
+    # its own, with its own CUDA stream, while this thread generates and deflates the next
+    # table (~25 ms of device time): the files of a rank are written side by side.
+    import threading
+    workers, failures = [], []
+
+    def in_background(write_file):
+        device = torch.cuda.current_device()
+
+        def run():
+            try:
+                torch.cuda.set_device(device)
+                with torch.cuda.stream(torch.cuda.Stream()):
+                    write_file()
+            except BaseException as e:   # noqa: BLE001 -- re-raised by the caller's thread
+                failures.append(e)
+
+        t = threading.Thread(target=run, name="iiv-table-writer")
+        t.start()
+        workers.append(t)
+
+    try:
+        for k in mine:
+            p, bitmap_cls, nominal, _ = jobs[k]
+            if p not in edps:
+                print("Processing palette %s" % p)
+                edps[p] = compute_substitute_costs(p)
+            make_edit_distance(p, edps[p], bitmap_cls, nominal, _writer=in_background)
+            written.append("%s/%s_palette_%d_edit_distance.npz"
+                           % (DATA_DIR, bitmap_cls.NAME, p.ID.value))
+    finally:
+        for t in workers:
+            t.join()
+    if failures:
+        raise failures[0]
     return written
 
 

@@ -1,6 +1,7 @@
 """GPU: the device-side deflate of a table (csrc/iiv_deflate.cu, next row N1) round-trips
 through zlib -- the reference's loader is np.load (screen.py:352) -- and its CRCs are right."""
 
+import os
 import zipfile
 import zlib
 
@@ -63,3 +64,27 @@ def test_make_edit_distance_file_is_a_plain_npz(ops, oracle_luts, tmp_path, monk
         assert z.testzip() is None
         assert z.getinfo("edit_distance.npy").file_size == want.nbytes + 128
     assert np.array_equal(npz_io.load_member(path, "edit_distance"), want)
+
+
+def test_main_writes_the_four_files_side_by_side(oracle_luts, tmp_path, monkeypatch):
+    """make_data_tables.main() (make_data_tables.py:191-204): every file is brought home and
+    written on a thread of its own while the next table is generated and deflated; each must
+    still be the oracle's table, and a second call over the same directory as well (staging
+    rings recycled)."""
+    import contextlib
+    import io
+    from iivision_b200 import make_data_tables as mdt, npz_io
+    from oracle import tables
+    monkeypatch.setattr(mdt, "DATA_DIR", str(tmp_path))
+    for _ in range(2):
+        with contextlib.redirect_stdout(io.StringIO()):
+            written = mdt.main(0, 1)
+        assert [os.path.basename(w) for w in written] == [
+            "HGR_palette_0_edit_distance.npz", "DHGR_palette_0_edit_distance.npz",
+            "HGR_palette_5_edit_distance.npz", "DHGR_palette_5_edit_distance.npz"]
+    for w in written:
+        mode, _, pid = os.path.basename(w).split("_")[:3]
+        want, _ = tables.build_table(mode, oracle_luts[int(pid)], triangular=True)
+        assert np.array_equal(npz_io.load_member(w, "edit_distance"), want), w
+        with zipfile.ZipFile(w) as z:
+            assert z.testzip() is None
