@@ -9,9 +9,9 @@
 // only, and those are fed by a 4-6 bit window of the masked value (colours.py:100-134:
 // pixel t rotates dots t..t+3; screen.py:741-789 for which bits feed which HGR dots).  So
 //     entry(x, y) = row0(T_0[x_0, y_0]) . T_1[x_1, y_1] . ... . T_{L-1}[..] . col(T_L[x_L, y_L])
-// with T_k tabulated over pairs of k-th windows: 2^8..2^12 pairs each, 104 KiB (DHGR) /
-// 106 KiB (HGR) per byte offset -- the two byte offsets of a bank fit the 227 KiB of shared
-// memory of one SM.  A lookup is then 5 (DHGR) / 9 (HGR) shared-memory loads and a few
+// with T_k tabulated over pairs of k-th windows: 2^10..2^12 pairs each, 104 KiB per byte
+// offset in both modes -- the two byte offsets of a bank fit the 227 KiB of shared
+// memory of one SM.  A lookup is then 5 (DHGR) / 8 (HGR) shared-memory loads and a few
 // packed 16-bit adds and mins instead of one 2-byte gather from a 512 MiB / 1 GiB table in
 // HBM (93 B of DRAM traffic each, profiles/r02_gather_flavours.txt): the scorer stops being
 // bound by DRAM row activations and the table is not needed at all.
@@ -42,21 +42,21 @@ template <int MODE, int WIN>
 struct Chain;
 template <>
 struct Chain<IIV_MODE_HGR, 0> {
-  static constexpr int kSegs = 9;
+  static constexpr int kSegs = 8;
   __host__ __device__ static constexpr SegDesc seg(int k) {
     constexpr SegDesc s[kSegs] = {{0, 2, 0x041f},  {2, 4, 0x043a},   {4, 6, 0x0478},
                                   {6, 8, 0x04f0},  {8, 10, 0x05e0},  {10, 12, 0x07c0},
-                                  {12, 13, 0x0780}, {13, 15, 0x1f80}, {15, 18, 0x3f00}};
+                                  {12, 15, 0x1f80}, {15, 18, 0x3f00}};
     return s[k];
   }
 };
 template <>
 struct Chain<IIV_MODE_HGR, 1> {
-  static constexpr int kSegs = 9;
+  static constexpr int kSegs = 8;
   __host__ __device__ static constexpr SegDesc seg(int k) {
     constexpr SegDesc s[kSegs] = {{0, 2, 0x003f},  {2, 4, 0x007a},   {4, 6, 0x00f8},
                                   {6, 8, 0x01e8},  {8, 10, 0x03c8},  {10, 12, 0x0788},
-                                  {12, 13, 0x0708}, {13, 15, 0x1f08}, {15, 18, 0x3e08}};
+                                  {12, 15, 0x1f08}, {15, 18, 0x3e08}};
     return s[k];
   }
 };
@@ -96,7 +96,7 @@ __host__ __device__ constexpr uint32_t seg_offset(int k) {   // k == kSegs: the 
 }
 template <int MODE>
 constexpr uint32_t kOffsetBytes = seg_offset<MODE, 0>(Chain<MODE, 0>::kSegs);
-static_assert(seg_offset<IIV_MODE_HGR, 1>(9) == kOffsetBytes<IIV_MODE_HGR>,
+static_assert(seg_offset<IIV_MODE_HGR, 1>(Chain<IIV_MODE_HGR, 1>::kSegs) == kOffsetBytes<IIV_MODE_HGR>,
               "both HGR window sets take the same room");
 static_assert(2 * kOffsetBytes<IIV_MODE_HGR> <= 227 * 1024 &&
                   2 * kOffsetBytes<IIV_MODE_DHGR> <= 227 * 1024,
@@ -244,7 +244,7 @@ score_frames_factored_kernel(const uint64_t* __restrict__ src, size_t src_stride
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t tables_bar;
   const int bank = blockIdx.x % kBanks;   // index into diff / priority: 0 main, 1 aux
-  // The bank's two tables come in as two TMA bulk copies (cp.async.bulk, 104 / 106 KiB each)
+  // The bank's two tables come in as two TMA bulk copies (cp.async.bulk, 104 KiB each)
   // that complete on an mbarrier; the block's threads meanwhile fetch the screen bytes, source
   // words and priorities of their first item and wait only when they need a table entry.
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tables_bar);

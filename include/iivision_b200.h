@@ -233,7 +233,7 @@ int iiv_score_frames(int mode, const uint64_t* d_source_packed, size_t source_st
 /* iiv_score_frames without the table.  An edit-distance entry (make_data_tables.py:92-108)
  * is a product of per-pixel 2x2 (min,+) matrices; the product over a segment of pixels is a
  * function of a 4-6 bit window of each masked value, so the entry can be evaluated from small
- * per-segment FACTOR tables (104 / 106 KiB per byte offset: a bank's two offsets live in one
+ * per-segment FACTOR tables (104 KiB per byte offset: a bank's two offsets live in one
  * SM's shared memory) instead of gathered from the 512 MiB / 1 GiB table in HBM.
  *   iiv_score_factors_bytes   size of the factor tables of a mode (all byte offsets, plus a
  *                             16-byte trailer: is the LUT's diagonal zero)
