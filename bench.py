@@ -960,9 +960,9 @@ def run_ours(args, rank, world, local_rank):
     ops.table_generate(MODE, lut, layout=ops.LAYOUT_SYMMETRIC, out=table)
     clocks = sampler.summary(t_load0, time.perf_counter()) if sampler else None
     # the generator's average duration over the TIMED REGION (CUDA events on its stream
-    # around the K back-to-back steps of this rank; a step = pixel_prologue, 3 us, +
-    # split_prologue, 8 us, + split_kernel, chained as programmatic dependent launches, so
-    # `achieved` charges the dominant kernel with both prologues).  The same step timed alone
+    # around the K back-to-back steps of this rank; a step = split_prologue, ~9 us,
+    # + split_kernel launched as its programmatic dependent, so `achieved` charges the
+    # dominant kernel with the prologue).  The same step timed alone
     # with a synchronize on both sides (kernel_ms_synced) is ~10 % longer: on an idle GPU the
     # three launches wait for the host to submit them.  The write-only fills below are timed
     # back to back like the steps, so frac_of_write_only compares like with like.
@@ -1102,8 +1102,8 @@ def run_ours(args, rank, world, local_rank):
                      "frac_of_write_only": achieved / max(fill_gbs.values()),
                      "note": "2 B stored per entry x entries per launch / average duration "
                              "of a step over the timed region (CUDA events on the launching "
-                             "stream around the K steps; split_kernel is 94 % of a step, its two "
-                             "prologues are charged to it); kernel_ms_synced = the same step "
+                             "stream around the K steps; split_kernel is 94 % of a step, its "
+                             "prologue is charged to it); kernel_ms_synced = the same step "
                              "timed alone between synchronizes (host submission exposed); peak = measured "
                              "copy (read+write) bandwidth, which a write-only stream can exceed: "
                              "write_only_gbs = cudaMemsetAsync and a one-16-byte-store-per-thread "

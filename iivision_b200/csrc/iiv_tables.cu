@@ -573,6 +573,26 @@ struct SplitDims {
 // A[o][xi][0][xj] = D_c, A[o][xi][1][xj] = D_{c-1} + 1 or INF (uint16);
 // B[o][yi][yj] = F_c | F_{c+1} << 16.  A thread takes one xi (yi) and the four xj (yj) that
 // differ in the late (early) bits.
+// The pixel strings of one value computed in registers (what pixel_prologue stores for the
+// chain and tree kernels): the split prologue needs five strings per thread and is bound by
+// latency, not issue slots -- deriving them costs less than the loads did, and the
+// pixel_prologue launch is gone (HGR step -2.5 %, DHGR -7 %).
+template <int MODE>
+__device__ __forceinline__ void make_pixels(int o, uint32_t v, uint64_t& lo, uint32_t& hi) {
+  using M = Mode<MODE>;
+  const uint32_t dots = to_dots<MODE>(v, o);
+  lo = 0;
+  hi = 0;
+#pragma unroll
+  for (int t = 0; t < M::kDots; ++t) {
+    const uint64_t p = nominal_pixel(dots, t, M::phase(o));
+    if (t < 16)
+      lo |= p << (4 * t);
+    else
+      hi |= (uint32_t)p << (4 * (t - 16));
+  }
+}
+
 template <int MODE, int WIN>
 __device__ __forceinline__ void split_tabulate(const uint8_t* S, int o, int which, uint32_t idx,
                                                uint16_t* ta, uint32_t* tb) {
@@ -590,9 +610,9 @@ __device__ __forceinline__ void split_tabulate(const uint8_t* S, int o, int whic
     static_assert(BL::count == 2, "two late bits");
     if (idx >= NA * NA / 4) return;
     const uint32_t xi = idx / (NA / 4), xj0 = BR::dep(idx % (NA / 4));
-    load_pixels<MODE>(o, BA::dep(xi), alo, ahi);
+    make_pixels<MODE>(o, BA::dep(xi), alo, ahi);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) load_pixels<MODE>(o, BA::dep(xj0 | BL::dep(v)), blo[v], bhi[v]);
+    for (int v = 0; v < 4; ++v) make_pixels<MODE>(o, BA::dep(xj0 | BL::dep(v)), blo[v], bhi[v]);
     uint32_t d2 = 0, d1 = 0, pa = 0, pb = 0;
 #pragma unroll
     for (int t = 0; t < W::kSharedA; ++t) {
@@ -623,9 +643,9 @@ __device__ __forceinline__ void split_tabulate(const uint8_t* S, int o, int whic
     static_assert(BE::count == 2, "two early bits");
     if (idx >= NB * NB / 4) return;
     const uint32_t yi = idx / (NB / 4), yj0 = BR::dep(idx % (NB / 4));
-    load_pixels<MODE>(o, BB::dep(yi), alo, ahi);
+    make_pixels<MODE>(o, BB::dep(yi), alo, ahi);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) load_pixels<MODE>(o, BB::dep(yj0 | BE::dep(v)), blo[v], bhi[v]);
+    for (int v = 0; v < 4; ++v) make_pixels<MODE>(o, BB::dep(yj0 | BE::dep(v)), blo[v], bhi[v]);
     uint32_t f1 = 0, f2 = 0, na = 0, nb = 0;   // F_{t+1}, F_{t+2}, pixels t+1
 #pragma unroll
     for (int t = n - 1; t >= W::kSharedB; --t) {
@@ -660,7 +680,6 @@ split_prologue(const __grid_constant__ Lut lut, uint16_t* __restrict__ ta,
   __syncthreads();
   const int o = blockIdx.z, which = blockIdx.y;
   const uint32_t idx = blockIdx.x * 256 + threadIdx.x;
-  grid_dependency_wait();   // the pixel strings
   if (MODE == IIV_MODE_HGR && o == 1)
     split_tabulate<MODE, SplitDims<MODE>::kWins - 1>(S, o, which, idx, ta, tb);
   else
@@ -788,13 +807,14 @@ int generate_split(const Lut& lut, const Dests& dests, uint32_t row_begin, uint3
   const dim3 grid((row_end - row_begin + rows_per_block - 1) / rows_per_block * groups,
                   M::kOffsets);
   const dim3 block(kSplitThreads);
-  // Both launches are programmatic dependents of the one before (pixel strings -> A / B
-  // tables -> generator): a launch's latency and its blocks' preamble hide behind its
-  // predecessor.  (One prologue + generator pair per offset, so that offset o + 1's tables are
+  // The generator is a programmatic dependent of the prologue (A / B tables -> generator):
+  // its launch latency and its blocks' preamble hide behind the prologue.  (One prologue + generator pair per offset, so that offset o + 1's tables are
   // made while offset o's rows drain, measured 3-8 % SLOWER: the second prologue is
   // latency-bound and the generator cannot start before it ends.)
-  cudaError_t launched = pdl_launch(split_prologue<MODE>, dim3(pairs / 4 / 256, 2, M::kOffsets),
-                                    dim3(256), st, lut, ta, tb);
+  // (The prologue itself is an ordinary launch: it overwrites scratch the previous call's
+  // generator may still be reading.)
+  split_prologue<MODE><<<dim3(pairs / 4 / 256, 2, M::kOffsets), 256, 0, st>>>(lut, ta, tb);
+  cudaError_t launched = cudaGetLastError();
   if (launched == cudaSuccess) {
     if (tri && multi)
       launched = pdl_launch(split_kernel<MODE, true, true>, grid, block, st, ta, tb, dests, row_begin, row_end);
@@ -872,6 +892,10 @@ int generate(const Lut& lut, const Dests& dests, uint32_t row_begin,
   IIV_REQUIRE(row_begin <= row_end && row_end <= N, "bad row range [%u,%u)",
               row_begin, row_end);
   if (row_begin == row_end) return 0;
+  const bool tri = layout == IIV_LAYOUT_TRIANGULAR, multi = dests.n > 1 || dests.multicast;
+  // the split generator derives the strings it needs in registers (no pixel-string table)
+  if (algo != IIV_ALGO_CHAIN && algo != IIV_ALGO_TREE)
+    return generate_split<MODE>(lut, dests, row_begin, row_end, tri, multi, st);
   pixel_prologue<MODE><<<dim3(N / 256, M::kOffsets), 256, 0, st>>>();
   IIV_LAUNCH_CHECK("pixel_prologue");
   if (algo == IIV_ALGO_CHAIN) {
@@ -883,8 +907,6 @@ int generate(const Lut& lut, const Dests& dests, uint32_t row_begin,
     IIV_LAUNCH_CHECK("chain_kernel");
     return 0;
   }
-  const bool tri = layout == IIV_LAYOUT_TRIANGULAR, multi = dests.n > 1 || dests.multicast;
-  if (algo != IIV_ALGO_TREE) return generate_split<MODE>(lut, dests, row_begin, row_end, tri, multi, st);
   const uint32_t tiles = ((row_end + 7) >> 3) - (row_begin >> 3);
   dim3 grid(N / (kTreeThreads * 8), (tiles + kTilesPerChunk - 1) / kTilesPerChunk,
             M::kOffsets);

@@ -129,9 +129,9 @@ def fill_probe(buf: torch.Tensor, variant: int = 0) -> None:
 
 
 def launches_per_table_generate() -> int:
-    """Kernels one iiv_table_generate call launches (pixel strings, the split generator's
-    A / B tables, the generator)."""
-    return 3
+    """Kernels one iiv_table_generate call launches (the split generator's A / B tables, the
+    generator)."""
+    return 2
 
 
 def generator_kernel_name() -> str:

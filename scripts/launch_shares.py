@@ -24,8 +24,8 @@ def main():
         print("%-64s %5d %12.1f us %5.1f%%" % (name[-64:], cnt[name], tot[name],
                                                100.0 * tot[name] / total))
     step = {k: tot[k] / cnt[k] for k in tot
-            if any(n in k for n in ("split_kernel<0, 0, 0>", "split_prologue<0>", "pixel_prologue<0>"))}
-    if len(step) == 3:
+            if any(n in k for n in ("split_kernel<0, 0, 0>", "split_prologue<0>"))}
+    if len(step) == 2:
         t = [v for k, v in step.items() if "split_kernel" in k][0]
         print("headline step = " + " + ".join("%s %.1f us" % (k.split("::")[-1], v)
                                               for k, v in sorted(step.items(), key=lambda kv: kv[1]))
